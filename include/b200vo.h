@@ -1,0 +1,171 @@
+/*
+ * b200vo.h -- C ABI of libb200vo.so: the B200 (sm_100a) replacement for the cv2 call
+ * sites on the reference's correspondence-and-pose hot path.
+ *
+ * Each entry point names the reference interface it replaces (file:line in
+ * ManuelWendl/Monocular_Visual_Odometry_VA4MR).  Plain pointers and sizes only; all
+ * pointers are caller-owned HOST memory unless the function name ends in `_dev`.
+ * Return value: 0 = OK; <0 = argument/contract violation (the condition under which cv2
+ * raises cv2.error, or B200VO_E_UNSUPPORTED for argument patterns the reference never
+ * uses -- there is NO CPU fallback); >0 = CUDA failure (text via b200vo_last_error).
+ * Algorithmic non-success (PnP found nothing, KLT lost a point) is not an error.
+ *
+ * One ctx = one CUDA device + one stream + its buffers; calls on a ctx are serialised by
+ * the caller and are synchronous at return (host outputs valid).
+ */
+#ifndef B200VO_H
+#define B200VO_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200vo_ctx b200vo_ctx;
+
+#define B200VO_OK 0
+#define B200VO_E_BADARG (-1)      /* cv2.error -215 equivalent */
+#define B200VO_E_UNSUPPORTED (-2) /* valid cv2 call, but not a pattern this path implements */
+#define B200VO_E_NOMEM (-3)
+
+/* ---- context ---- */
+int b200vo_create(int device, b200vo_ctx** out);
+void b200vo_destroy(b200vo_ctx* ctx);
+const char* b200vo_last_error(b200vo_ctx* ctx);
+/* ABI/version probe: returns 100*major+minor; also the compiled sm arch in *sm_arch (e.g. 100). */
+int b200vo_version(int* sm_arch);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+long long b200vo_launch_count(b200vo_ctx* ctx);
+/* Elapsed device time (ms, CUDA events on the ctx stream) of the last API call's GPU work. */
+float b200vo_last_gpu_ms(b200vo_ctx* ctx);
+
+/*
+ * Replaces cv2.calcOpticalFlowPyrLK(prevImg, nextImg, prevPts, None, winSize=, maxLevel=,
+ * criteria=) at VisualOdometryPipeLine.py:281 and :287.
+ * prev/next: uint8 rows x cols with row strides in bytes; prev_pts: float32 (n,2).
+ * Outputs: next_pts float32 (n,2), status uint8 (n), err float32 (n).
+ * crit_type: bit0 = COUNT, bit1 = EPS (cv2.TERM_CRITERIA_*).  flags must be 0.
+ */
+int b200vo_calc_optical_flow_pyr_lk(b200vo_ctx* ctx, const uint8_t* prev, const uint8_t* next,
+                                    int rows, int cols, size_t prev_step, size_t next_step,
+                                    const float* prev_pts, int n, int win_w, int win_h,
+                                    int max_level, int crit_type, int crit_max_count,
+                                    double crit_eps, int flags, double min_eig_thr,
+                                    float* next_pts, uint8_t* status, float* err);
+
+/*
+ * Frame-slot form of the same call (device-resident pyramids; what the identity-caching
+ * shim and the per-frame loop use so that `prev` is not re-uploaded / re-built 4x per frame
+ * as cv2 does).  Slots 0..B200VO_MAX_SLOTS-1.
+ */
+#define B200VO_MAX_SLOTS 4
+int b200vo_frame_upload(b200vo_ctx* ctx, int slot, const uint8_t* img, int rows, int cols,
+                        size_t step, int win_w, int win_h, int max_level);
+int b200vo_klt_slots(b200vo_ctx* ctx, int prev_slot, int next_slot, const float* prev_pts, int n,
+                     int win_w, int win_h, int max_level, int crit_type, int crit_max_count,
+                     double crit_eps, int flags, double min_eig_thr,
+                     float* next_pts, uint8_t* status, float* err);
+/* Test hook: copy pyramid level `level` of `slot` (without border) to host (tight rows). */
+int b200vo_frame_download_level(b200vo_ctx* ctx, int slot, int level, uint8_t* out, int* w, int* h,
+                                int* n_levels);
+
+/*
+ * Replaces cv2.goodFeaturesToTrack(img, maxCorners, qualityLevel, minDistance, blockSize=3,
+ * useHarrisDetector=False, mask=None) at VisualOdometryPipeLine.py:256.
+ * corners_xy: float32 (max_corners,2) caller-allocated; *n_out = corners found (0 -> None).
+ */
+int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img, int rows, int cols,
+                                  size_t step, int max_corners, double quality, double min_dist,
+                                  int block_size, float* corners_xy, int* n_out);
+
+/*
+ * Replaces cv2.BFMatcher().knnMatch(desc0, desc1, k=2) at :229 plus the Lowe ratio loop at
+ * :218-224.  q (nq,dim), t (nt,dim) float32 row-major, integer-valued 0..255 (SIFT).
+ * idx2 int32 (nq,2) (-1 when nt<2), dist2 float32 (nq,2), accept uint8 (nq).
+ */
+int b200vo_knn2_ratio(b200vo_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                      double ratio, int32_t* idx2, float* dist2, uint8_t* accept);
+
+/*
+ * Replaces cv2.findEssentialMat(p1, p2, K, method=RANSAC, prob, threshold) at :308.
+ * p1,p2 float32 (n,2); K row-major 3x3.  E row-major 3x3, mask uint8 (n), *found = 0/1.
+ */
+int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1, const float* p2, int n,
+                                     const double K[9], double prob, double thr, int max_iters,
+                                     double E[9], uint8_t* mask, int* found);
+
+/*
+ * Replaces cv2.solvePnPRansac(obj, img, K, zeros(4), flags=SOLVEPNP_P3P, confidence=,
+ * reprojectionError=, iterationsCount=) at :343 (incl. cv2's EPnP refit on the inliers).
+ * obj float32 (n,3), img float32 (n,2).  inliers int32 (n) caller-allocated, ascending,
+ * *n_inliers valid entries.  *success = 0 -> rvec/tvec unspecified, n_inliers = 0.
+ */
+int b200vo_solve_pnp_ransac_p3p(b200vo_ctx* ctx, const float* obj, const float* img, int n,
+                                const double K[9], int iters, float reproj_err, double conf,
+                                double rvec[3], double tvec[3], int32_t* inliers, int* n_inliers,
+                                int* success);
+/* Same, but with the hypothesis sample set supplied by the caller (parity tests: "same
+ * hypothesis sample set"): samples int32 (iters,4). */
+int b200vo_solve_pnp_ransac_p3p_samples(b200vo_ctx* ctx, const float* obj, const float* img, int n,
+                                        const double K[9], const int32_t* samples, int iters,
+                                        float reproj_err, double conf, double rvec[3],
+                                        double tvec[3], int32_t* inliers, int* n_inliers,
+                                        int* success, int32_t* counts_out /* iters or NULL */,
+                                        int* winner_iter, int* iters_run);
+
+/*
+ * Batched per-frame hot path for independent sequences (BASELINE config 5): for each of
+ * `batch` sequences, KLT on the landmark keypoints and on the candidate keypoints
+ * (:281,:287) from the sequence's previous frame (kept resident from the previous step) to
+ * its new frame, then P3P-RANSAC + EPnP on the tracked landmarks (:343).
+ * Host arrays are [batch]-major; see INTEGRATION.md for the exact layout.
+ */
+typedef struct b200vo_batch b200vo_batch;
+typedef struct {
+    int rows, cols;
+    int win_w, win_h, max_level, crit_type, crit_max_count;
+    double crit_eps, min_eig_thr;
+    int pnp_iters;
+    float pnp_reproj_err;
+    double pnp_conf;
+    double K[9];
+    int max_landmarks;  /* capacity per sequence */
+    int max_candidates; /* capacity per sequence */
+} b200vo_batch_cfg;
+
+int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batch_cfg* cfg, b200vo_batch** out);
+void b200vo_batch_destroy(b200vo_batch* b);
+/* Upload the first frame of every sequence (frames: batch x rows x cols, tight). */
+int b200vo_batch_prime(b200vo_batch* b, const uint8_t* frames);
+/*
+ * One step.  frames: batch x rows x cols uint8 (new frame per sequence).
+ * lm_pts float32 (batch,max_landmarks,2), lm_obj float32 (batch,max_landmarks,3), n_lm int32 (batch);
+ * cand_pts float32 (batch,max_candidates,2), n_cand int32 (batch).
+ * Outputs: lm_next/lm_status/cand_next/cand_status shaped like the inputs;
+ * pose double (batch,6) = rvec|tvec; pnp_ok uint8 (batch); inlier_mask uint8 (batch,max_landmarks)
+ * over the landmark slots (0 for untracked); n_inliers int32 (batch).
+ * The new frame becomes the sequence's previous frame for the next step.
+ */
+int b200vo_batch_step(b200vo_batch* b, const uint8_t* frames, const float* lm_pts,
+                      const float* lm_obj, const int32_t* n_lm, const float* cand_pts,
+                      const int32_t* n_cand, float* lm_next, uint8_t* lm_status, float* cand_next,
+                      uint8_t* cand_status, double* pose, uint8_t* pnp_ok, uint8_t* inlier_mask,
+                      int32_t* n_inliers);
+/* Same step with every input already resident in device memory and outputs left there
+ * (bench.py `value`: no host<->device copies in the timed region).  Asynchronous on the
+ * ctx stream; pair with b200vo_sync. */
+int b200vo_batch_step_dev(b200vo_batch* b, const uint8_t* frames_dev, const float* lm_pts_dev,
+                          const float* lm_obj_dev, const int32_t* n_lm_dev,
+                          const float* cand_pts_dev, const int32_t* n_cand_dev, float* lm_next_dev,
+                          uint8_t* lm_status_dev, float* cand_next_dev, uint8_t* cand_status_dev,
+                          double* pose_dev, uint8_t* pnp_ok_dev, uint8_t* inlier_mask_dev,
+                          int32_t* n_inliers_dev);
+int b200vo_sync(b200vo_ctx* ctx);
+/* Raw stream handle (cudaStream_t) so callers can record CUDA events on the launching stream. */
+void* b200vo_stream(b200vo_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

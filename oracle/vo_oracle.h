@@ -1,0 +1,80 @@
+/*
+ * oracle/vo_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C) of the arithmetic behind the reference's hot-path
+ * cv2 call sites (reference VisualOdometryPipeLine.py:229,256,281,287,308,343).
+ * The arithmetic itself lives in OpenCV (third-party, `opencv-python`, pinned
+ * ==4.6.0.66 in reference requirements.txt:6; the oracle is pinned against the
+ * installed cv2 4.13.0 -- see tests/test_oracle_*.py and tests/golden/).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+ * load this library.  The product path (monocular_visual_odometry_va4mr_b200/)
+ * never does.
+ */
+#ifndef VO_ORACLE_H
+#define VO_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- pyramid / derivatives ---- */
+void orc_pyr_down_u8(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep);
+void orc_scharr_s16(const uint8_t* src, int w, int h, size_t sstep, int16_t* dst /* h*w*2 interleaved */);
+/* number of pyramid levels (incl. level 0) cv2 builds for (w,h,win,maxLevel) */
+int orc_pyr_levels(int w, int h, int win_w, int win_h, int max_level);
+
+/* ---- pyramidal LK (ref :281,:287) ---- */
+int orc_calc_optical_flow_pyr_lk(const uint8_t* prev, const uint8_t* next, int rows, int cols,
+                                 size_t prev_step, size_t next_step,
+                                 const float* prev_pts, int n, int win_w, int win_h, int max_level,
+                                 int crit_type, int crit_max_count, double crit_eps,
+                                 int flags, double min_eig_thr,
+                                 float* next_pts, uint8_t* status, float* err, int32_t* iters_out);
+
+/* ---- Shi-Tomasi (ref :256) ---- */
+void orc_min_eig_map(const uint8_t* img, int w, int h, size_t step, int block, float* eig);
+int orc_good_features_to_track(const uint8_t* img, int rows, int cols, size_t step, int max_corners,
+                               double quality, double min_dist, int block_size,
+                               float* corners_xy, int* n_out);
+
+/* ---- brute-force kNN(k=2) + ratio (ref :229, :218-224) ---- */
+int orc_knn2_ratio(const float* q, int nq, const float* t, int nt, int dim, double ratio,
+                   int32_t* idx2, float* dist2, uint8_t* accept);
+
+/* ---- RANSAC framework ---- */
+void orc_ransac_subsets(int count, int model_points, int n_iters, int32_t* subsets);
+int orc_ransac_update_num_iters(double p, double ep, int model_points, int max_iters);
+/* Replays cv2's sequential loop over per-model inlier counts.  counts[iter*max_models+m],
+ * nmodels[iter].  Returns winning flat index (iter*max_models+m) or -1; *iters_run = loop trips. */
+int orc_ransac_select(const int32_t* counts, const int32_t* nmodels, int max_models, int max_iters,
+                      int n_points, int model_points, double conf, int* iters_run);
+
+/* ---- PnP (ref :343) ---- */
+/* P3P on 3 correspondences: object X[3][3], normalised image rays (x,y,1) -> up to 4 (R,t). */
+int orc_p3p(const double X[9], const double xn[6], double R[4][9], double t[4][3]);
+/* 4-point minimal solve as cv2's PnPRansacCallback: returns 1 and [rvec|tvec] or 0. */
+int orc_pnp_minimal(const float* obj4, const float* img4, const double K[9], double rvec[3], double tvec[3]);
+/* reprojection errors as cv2 computeError: FP64 project, round to f32, f32 squared error. */
+void orc_pnp_errors(const float* obj, const float* img, int n, const double K[9],
+                    const double rvec[3], const double tvec[3], float* err);
+void orc_rodrigues_to_R(const double rvec[3], double R[9]);
+void orc_R_to_rodrigues(const double R[9], double rvec[3]);
+int orc_epnp(const double* obj, const double* img, int n, const double K[9], double R[9], double t[3]);
+int orc_solve_pnp_ransac_p3p(const float* obj, const float* img, int n, const double K[9], int iters,
+                             float reproj_err, double conf, double rvec[3], double tvec[3],
+                             int32_t* inliers, int* n_inliers, int* success, int* iters_run);
+
+/* ---- essential matrix (ref :308) ---- */
+int orc_five_point(const double x1[10], const double x2[10], double E[10][9]);
+void orc_sampson_errors(const double* x1n, const double* x2n, int n, const double E[9], float* err);
+int orc_find_essential_mat_ransac(const float* p1, const float* p2, int n, const double K[9],
+                                  double prob, double thr, int max_iters, double E[9],
+                                  uint8_t* mask, int* found, int* iters_run);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
