@@ -44,7 +44,72 @@ def klt_small():
     np.savez_compressed(os.path.join(OUT, "klt_small.npz"), **out)
 
 
-ALL = dict(klt_small=klt_small)
+def make_pnp_case(n, out_frac, seed, noise=0.3, shape="kitti"):
+    """Landmarks in a corridor-like volume, projected with the frame-7 pose, N(0,noise) px noise,
+    `out_frac` gross outliers (+-60 px uniform).  float32 arrays as the reference passes them."""
+    rng = np.random.default_rng(seed)
+    K, w, h, step, _ = synth.SHAPES[shape]
+    Xc = np.column_stack([rng.uniform(-8, 8, n), rng.uniform(-2, 1.6, n), rng.uniform(4, 80, n)])
+    R_cw, c = synth.Corridor.pose(7, step)
+    Xw = c[None] + Xc @ R_cw.T
+    uv = synth.project(K, R_cw, c, Xw) + rng.normal(0, noise, (n, 2))
+    no = int(out_frac * n)
+    idx = rng.choice(n, no, replace=False)
+    uv[idx] += rng.uniform(-60, 60, (no, 2))
+    return Xw.astype(np.float32), uv.astype(np.float32), K.copy()
+
+
+PNP_CASES = [  # n, outlier fraction, seed, iterationsCount, reprojectionError
+    (2000, 0.1, 0, 500, 8.0), (2000, 0.5, 1, 500, 8.0), (1000, 0.3, 2, 500, 5.0), (983, 0.2, 3, 2000, 8.0),
+    (2000, 0.3, 5, 500, 8.0), (500, 0.7, 6, 500, 5.0), (73, 0.2, 7, 500, 8.0), (8, 0.0, 8, 500, 8.0),
+    (300, 0.85, 9, 500, 8.0), (4, 0.0, 10, 500, 8.0), (5000, 0.6, 4, 2000, 8.0), (40, 1.0, 11, 50, 2.0),
+]
+
+
+def pnp():
+    out = dict(cases=np.array(PNP_CASES, np.float64))
+    for ci, (n, of, seed, iters, thr) in enumerate(PNP_CASES):
+        obj, img, K = make_pnp_case(n, of, seed)
+        ok, rv, tv, inl = cv2.solvePnPRansac(obj, img, K, np.zeros(4), flags=cv2.SOLVEPNP_P3P, confidence=0.99,
+                                             reprojectionError=thr, iterationsCount=iters)
+        out[f"c{ci}_obj"], out[f"c{ci}_img"], out[f"c{ci}_K"] = obj, img, K
+        out[f"c{ci}_ok"] = np.array(bool(ok))
+        out[f"c{ci}_rvec"], out[f"c{ci}_tvec"] = rv, tv
+        out[f"c{ci}_inliers"] = inl if inl is not None else np.zeros((0, 1), np.int32)
+    # minimal-solver vectors: cv2.solvePnP(flags=P3P) on 4-point samples (some with an outlier)
+    obj, img, K = make_pnp_case(400, 0.3, 21)
+    rng = np.random.default_rng(5)
+    S = np.stack([rng.choice(400, 4, replace=False) for _ in range(300)]).astype(np.int32)
+    oks, rvs, tvs = [], [], []
+    for smp in S:
+        try:
+            ok, rv, tv = cv2.solvePnP(obj[smp], img[smp], K, np.zeros(4), flags=cv2.SOLVEPNP_P3P)
+        except cv2.error:
+            ok, rv, tv = False, np.zeros((3, 1)), np.zeros((3, 1))
+        fin = bool(ok) and np.all(np.isfinite(tv)) and np.all(np.isfinite(rv))
+        oks.append(fin); rvs.append(rv.ravel() if fin else np.zeros(3)); tvs.append(tv.ravel() if fin else np.zeros(3))
+    out.update(min_obj=obj, min_img=img, min_K=K, min_samples=S, min_ok=np.array(oks), min_rvec=np.array(rvs),
+               min_tvec=np.array(tvs))
+    # reprojection errors (cv2.projectPoints, float32 output) for one pose
+    ok, rv, tv, _ = cv2.solvePnPRansac(obj, img, K, np.zeros(4), flags=cv2.SOLVEPNP_P3P, reprojectionError=8.0, iterationsCount=100)
+    proj, _ = cv2.projectPoints(obj, rv, tv, K, np.zeros(4))
+    d = img - proj.reshape(-1, 2)
+    out.update(err_rvec=rv, err_tvec=tv, err_vals=(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32))
+    # EPnP refit vectors (float64 inputs, as solvePnPRansac feeds it)
+    for ei, (n, seed, noise) in enumerate([(200, 0, 0.3), (1000, 1, 0.3), (6, 4, 0.3), (1000, 5, 2.0), (50, 3, 0.0)]):
+        o, i, K = make_pnp_case(n, 0.0, seed, noise)
+        ok, rv, tv = cv2.solvePnP(o.astype(np.float64), i.astype(np.float64), K, np.zeros(4), flags=cv2.SOLVEPNP_EPNP)
+        out[f"e{ei}_obj"], out[f"e{ei}_img"], out[f"e{ei}_K"], out[f"e{ei}_rvec"], out[f"e{ei}_tvec"] = o, i, K, rv, tv
+    # cv::RNG known answers and SVD sign convention
+    svd_in = np.random.default_rng(3).normal(0, 3, (20, 3, 3))
+    svd_in = np.einsum("nij,nkj->nik", svd_in, svd_in)
+    out["svd_in"] = svd_in
+    out["svd_u"] = np.stack([cv2.SVDecomp(m)[1] for m in svd_in])
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(OUT, "pnp.npz"), **out)
+
+
+ALL = dict(klt_small=klt_small, pnp=pnp)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(ALL)
