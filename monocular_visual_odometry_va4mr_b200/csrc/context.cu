@@ -88,6 +88,7 @@ extern "C" void b200vo_destroy(b200vo_ctx* ctx)
     for (auto& b : ctx->d_stage_img) if (b.p) cudaFree(b.p);
     for (auto& b : ctx->d_scratch) if (b.p) cudaFree(b.p);
     for (auto& s : ctx->slots) if (s.slab.p) cudaFree(s.slab.p);
+    if (ctx->d_rng.p) cudaFree(ctx->d_rng.p);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);

@@ -1,0 +1,40 @@
+// Argument block shared by the PnP-RANSAC kernels (all pointers are device memory).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+
+struct b200vo_ctx;
+
+struct PnpArgs {
+    int batch, cap, iters;
+    const float* obj;       // [batch][cap][3]
+    const float* img;       // [batch][cap][2]
+    const int* n;           // [batch] live correspondences per sequence
+    double fx, fy, cx, cy;
+    float thr_sq;           // (float)(reprojectionError^2)
+    double conf;
+    const uint32_t* rng_raw;  // raw cv::RNG((uint64)-1) outputs
+    int n_raw;
+    // workspace
+    int* samples;           // [batch][iters][4]   (-1 = no sample)
+    double* hyp;            // [batch][iters][12]  R (row-major) | t
+    double* hyp_rvec;       // [batch][iters][3]
+    int* hyp_ok;            // [batch][iters]
+    int* counts;            // [batch][iters]
+    int* winner;            // [batch]
+    int* iters_run;         // [batch]
+    int* n_inliers;         // [batch]
+    int* flags;             // [batch] bit0: raw RNG table exhausted
+    // outputs
+    int* inliers;           // [batch][cap] ascending indices
+    uint8_t* mask;          // [batch][cap]
+    double* pose;           // [batch][6] rvec | tvec
+    uint8_t* ok;            // [batch]
+};
+
+void vo_rng_raw_stream(uint32_t* out, int n);
+size_t vo_pnp_workspace_bytes(int batch, int cap, int iters);
+void vo_pnp_carve_workspace(PnpArgs& a, void* ws);
+int vo_pnp_launch(b200vo_ctx* ctx, const PnpArgs& a, bool gen_samples);
+// device table of the raw RNG stream, at least n values (grown on demand, owned by ctx)
+int vo_rng_table(b200vo_ctx* ctx, int n, const uint32_t** d_table);
