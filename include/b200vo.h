@@ -161,7 +161,18 @@ int b200vo_batch_step_dev(b200vo_batch* b, const uint8_t* frames_dev, const floa
                           uint8_t* lm_status_dev, float* cand_next_dev, uint8_t* cand_status_dev,
                           double* pose_dev, uint8_t* pnp_ok_dev, uint8_t* inlier_mask_dev,
                           int32_t* n_inliers_dev);
+/* Per-stage device timing of batch steps (CUDA events on the ctx stream).  Stages:
+ * 0 = pyramid build, 1 = KLT kernel, 2 = compaction + PnP-RANSAC + EPnP + mask scatter. */
+#define B200VO_PROF_STAGES 3
+#define B200VO_PROF_RING 512
+int b200vo_batch_profile(b200vo_batch* b, int enable);
+/* Sums the recorded stage times (ms) over the *n_steps profiled steps since the last enable. */
+int b200vo_batch_profile_read(b200vo_batch* b, float* stage_ms /* [B200VO_PROF_STAGES] */, int* n_steps);
 int b200vo_sync(b200vo_ctx* ctx);
+/* Page-locked host memory for frame buffers: b200vo_batch_step DMAs straight out of such a
+ * buffer (pageable memory is staged through an internal pinned copy first). */
+void* b200vo_host_alloc(b200vo_ctx* ctx, size_t bytes);
+void b200vo_host_free(b200vo_ctx* ctx, void* p);
 /* Raw stream handle (cudaStream_t) so callers can record CUDA events on the launching stream. */
 void* b200vo_stream(b200vo_ctx* ctx);
 

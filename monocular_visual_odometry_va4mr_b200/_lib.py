@@ -70,7 +70,11 @@ SIGNATURES = {
         C.c_void_p, c_u8p, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p, c_f32p, c_u8p, c_f32p, c_u8p,
         c_f64p, c_u8p, c_u8p, c_i32p]),
     "b200vo_batch_step_dev": (C.c_int, [C.c_void_p] + [C.c_void_p] * 14),
+    "b200vo_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200vo_batch_profile_read": (C.c_int, [C.c_void_p, c_f32p, c_intp]),
     "b200vo_sync": (C.c_int, [C.c_void_p]),
+    "b200vo_host_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+    "b200vo_host_free": (None, [C.c_void_p, C.c_void_p]),
     "b200vo_stream": (C.c_void_p, [C.c_void_p]),
 }
 

@@ -1,0 +1,116 @@
+"""Batched per-frame hot path over independent sequences (BASELINE config 5).
+
+``SequenceBatch`` wraps ``b200vo_batch_*`` (include/b200vo.h): per step and per sequence it
+does what the reference's ``continuous_operation`` does on its hot path -- KLT on the landmark
+keypoints and on the candidate keypoints (``VisualOdometryPipeLine.py:281,:287``), keep
+``status == 1`` (``:282-284``), P3P-RANSAC + EPnP on the tracked landmarks (``:343``) -- for
+``batch`` sequences in one set of kernel launches, with the previous frames' pyramids resident
+in HBM.  torch is used only as a device-buffer allocator for the ``*_dev`` form.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BatchCfg, c_f32p, c_f64p, c_i32p, c_u8p
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class SequenceBatch:
+    def __init__(self, batch, rows, cols, K, win=(15, 15), max_level=5, criteria=(3, 50, 0.01),
+                 min_eig_thr=1e-4, pnp_iters=500, pnp_reproj_err=8.0, pnp_conf=0.99,
+                 max_landmarks=1024, max_candidates=1024, ctx: _lib.Context | None = None):
+        self.ctx = ctx or _lib.default_context(0)
+        self.batch, self.rows, self.cols = int(batch), int(rows), int(cols)
+        self.L, self.Cn = int(max_landmarks), int(max_candidates)
+        cfg = BatchCfg()
+        cfg.rows, cfg.cols = self.rows, self.cols
+        cfg.win_w, cfg.win_h, cfg.max_level = int(win[0]), int(win[1]), int(max_level)
+        cfg.crit_type, cfg.crit_max_count, cfg.crit_eps = int(criteria[0]), int(criteria[1]), float(criteria[2])
+        cfg.min_eig_thr = float(min_eig_thr)
+        cfg.pnp_iters, cfg.pnp_reproj_err, cfg.pnp_conf = int(pnp_iters), float(pnp_reproj_err), float(pnp_conf)
+        Kf = np.asarray(K, np.float64).reshape(9)
+        for i in range(9):
+            cfg.K[i] = float(Kf[i])
+        cfg.max_landmarks, cfg.max_candidates = self.L, self.Cn
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.ctx.lib.b200vo_batch_create(self.ctx.h, self.batch, C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise _lib.B200VOError(f"b200vo_batch_create failed ({rc}): {self.ctx.last_error()}")
+        self.h = h
+        # host outputs (reused)
+        b, L, Cn = self.batch, self.L, self.Cn
+        self.lm_next = np.zeros((b, L, 2), np.float32)
+        self.lm_status = np.zeros((b, L), np.uint8)
+        self.cand_next = np.zeros((b, max(Cn, 1), 2), np.float32)
+        self.cand_status = np.zeros((b, max(Cn, 1)), np.uint8)
+        self.pose = np.zeros((b, 6), np.float64)
+        self.pnp_ok = np.zeros((b,), np.uint8)
+        self.inlier_mask = np.zeros((b, L), np.uint8)
+        self.n_inliers = np.zeros((b,), np.int32)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.b200vo_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise _lib.B200VOError(f"{what} failed ({rc}): {self.ctx.last_error()}")
+
+    def pinned_frames(self, n_sets: int = 1) -> np.ndarray:
+        """(n_sets, batch, rows, cols) uint8 array in page-locked memory (b200vo_host_alloc)."""
+        nbytes = n_sets * self.batch * self.rows * self.cols
+        ptr = self.ctx.lib.b200vo_host_alloc(self.ctx.h, nbytes)
+        if not ptr:
+            raise MemoryError("b200vo_host_alloc")
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, np.uint8).reshape(n_sets, self.batch, self.rows, self.cols)
+        self._pinned = getattr(self, "_pinned", []) + [ptr]
+        return arr
+
+    def prime(self, frames: np.ndarray):
+        frames = np.ascontiguousarray(frames, np.uint8).reshape(self.batch, self.rows, self.cols)
+        self._chk(self.ctx.lib.b200vo_batch_prime(self.h, _p(frames, c_u8p)), "b200vo_batch_prime")
+
+    def step(self, frames, lm_pts, lm_obj, n_lm, cand_pts=None, n_cand=None):
+        """Host buffers in, host buffers out (synchronous).  Returns a dict of views on reused arrays."""
+        b, L, Cn = self.batch, self.L, self.Cn
+        assert frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.size == b * self.rows * self.cols
+        assert lm_pts.dtype == np.float32 and lm_pts.shape == (b, L, 2) and lm_pts.flags.c_contiguous
+        assert lm_obj.dtype == np.float32 and lm_obj.shape == (b, L, 3) and lm_obj.flags.c_contiguous
+        assert n_lm.dtype == np.int32 and n_lm.shape == (b,)
+        if Cn > 0:
+            assert cand_pts is not None and cand_pts.dtype == np.float32 and cand_pts.shape == (b, Cn, 2)
+            assert n_cand is not None and n_cand.dtype == np.int32 and n_cand.shape == (b,)
+        rc = self.ctx.lib.b200vo_batch_step(
+            self.h, _p(frames, c_u8p), _p(lm_pts, c_f32p), _p(lm_obj, c_f32p), _p(n_lm, c_i32p),
+            _p(cand_pts, c_f32p) if Cn > 0 else None, _p(n_cand, c_i32p) if Cn > 0 else None,
+            _p(self.lm_next, c_f32p), _p(self.lm_status, c_u8p), _p(self.cand_next, c_f32p),
+            _p(self.cand_status, c_u8p), _p(self.pose, c_f64p), _p(self.pnp_ok, c_u8p),
+            _p(self.inlier_mask, c_u8p), _p(self.n_inliers, c_i32p))
+        self._chk(rc, "b200vo_batch_step")
+        return dict(lm_next=self.lm_next, lm_status=self.lm_status, cand_next=self.cand_next,
+                    cand_status=self.cand_status, pose=self.pose, pnp_ok=self.pnp_ok,
+                    inlier_mask=self.inlier_mask, n_inliers=self.n_inliers)
+
+    def step_dev(self, frames_dev, lm_pts_dev, lm_obj_dev, n_lm_dev, cand_pts_dev, n_cand_dev, out_dev: dict):
+        """Device pointers in/out (ints from tensor.data_ptr()); asynchronous on the ctx stream."""
+        o = out_dev
+        rc = self.ctx.lib.b200vo_batch_step_dev(
+            self.h, frames_dev, lm_pts_dev, lm_obj_dev, n_lm_dev, cand_pts_dev, n_cand_dev,
+            o["lm_next"], o["lm_status"], o["cand_next"], o["cand_status"], o["pose"], o["pnp_ok"],
+            o["inlier_mask"], o["n_inliers"])
+        self._chk(rc, "b200vo_batch_step_dev")

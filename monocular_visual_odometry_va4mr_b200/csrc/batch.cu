@@ -1,0 +1,350 @@
+// Batched per-frame hot path for independent sequences (BASELINE config 5): per sequence and
+// frame the reference runs calcOpticalFlowPyrLK on the landmark keypoints and on the candidate
+// keypoints (VisualOdometryPipeLine.py:281,:287), keeps status==1 (:282-284), then
+// solvePnPRansac on the surviving landmarks (:343).  Here one launch of each kernel covers every
+// sequence of the batch, the previous frame's pyramid stays resident in HBM between steps, and
+// nothing returns to the host between KLT and PnP.
+#include "internal.cuh"
+#include "pnp.cuh"
+
+struct b200vo_batch {
+    b200vo_ctx* ctx;
+    int batch;
+    b200vo_batch_cfg cfg;
+    PyrGeom geom;
+    KltParams kp;
+    int cur;                 // slab set holding the previous frames
+    DevBuf slabs[2];         // [batch] pyramids each
+    DevBuf raw;              // device copy of the uploaded frames (host-input path)
+    DevBuf pts_in;           // host-input path: lm_pts | lm_obj | n_lm | cand_pts | n_cand
+    DevBuf outs;             // host-input path: outputs
+    DevBuf work;             // compacted landmarks + PnP workspace
+    // carved from `work`
+    float* c_obj; float* c_img; int* c_n; int* c_orig; int* inliers; uint8_t* c_mask;
+    void* pnp_ws;
+    const uint32_t* rng; int n_raw;
+    bool primed;
+    // optional per-kernel timing (CUDA events on the ctx stream): [step][stage] boundaries
+    bool profile = false;
+    int prof_n = 0;
+    cudaEvent_t prof_ev[B200VO_PROF_RING][B200VO_PROF_STAGES + 1];
+    bool prof_init = false;
+};
+
+static void prof_mark(b200vo_batch* B, int stage)
+{
+    if (!B->profile || B->prof_n >= B200VO_PROF_RING) return;
+    cudaEventRecord(B->prof_ev[B->prof_n][stage], B->ctx->stream);
+}
+
+// status==1 landmarks, in order, into the compact PnP input arrays (what `matched_pts[tracked]`
+// does in the reference, :282-284)
+__global__ void __launch_bounds__(256)
+compact_tracked_kernel(int cap, const int* __restrict__ n_lm, const float* __restrict__ lm_next,
+                       const uint8_t* __restrict__ lm_status, const float* __restrict__ lm_obj,
+                       float* __restrict__ c_obj, float* __restrict__ c_img, int* __restrict__ c_n,
+                       int* __restrict__ c_orig)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int b = blockIdx.x;
+    const int n = n_lm[b];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const size_t gi = (size_t)b * cap + i;
+        const bool keep = i < n && lm_status[gi] == 1;
+        const unsigned bm = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(bm);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (keep) {
+            const size_t o = (size_t)b * cap + off + __popc(bm & ((1u << lane) - 1));
+            c_obj[3 * o] = lm_obj[3 * gi]; c_obj[3 * o + 1] = lm_obj[3 * gi + 1]; c_obj[3 * o + 2] = lm_obj[3 * gi + 2];
+            c_img[2 * o] = lm_next[2 * gi]; c_img[2 * o + 1] = lm_next[2 * gi + 1];
+            c_orig[o] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) c_n[b] = s_base;
+}
+
+// inlier mask over the ORIGINAL landmark slots
+__global__ void __launch_bounds__(256)
+scatter_mask_kernel(int cap, const uint8_t* __restrict__ ok, const int* __restrict__ n_inl,
+                    const int* __restrict__ inliers, const int* __restrict__ c_orig,
+                    uint8_t* __restrict__ mask_out, int* __restrict__ n_inl_out, uint8_t* __restrict__ ok_out)
+{
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) mask_out[(size_t)b * cap + i] = 0;
+    __syncthreads();
+    const int m = ok[b] ? n_inl[b] : 0;
+    for (int k = threadIdx.x; k < m; k += blockDim.x)
+        mask_out[(size_t)b * cap + c_orig[(size_t)b * cap + inliers[(size_t)b * cap + k]]] = 1;
+    if (threadIdx.x == 0) { n_inl_out[b] = m; ok_out[b] = ok[b]; }
+}
+
+extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batch_cfg* cfg, b200vo_batch** out)
+{
+    if (!ctx || !cfg || !out || batch <= 0) return B200VO_E_BADARG;
+    *out = nullptr;
+    if (cfg->max_level < 0 || cfg->win_w <= 2 || cfg->win_h <= 2 || cfg->rows <= 0 || cfg->cols <= 0)
+        return vo_set_err(ctx, B200VO_E_BADARG, "maxLevel >= 0 && winSize.width > 2 && winSize.height > 2");
+    if (cfg->win_w >= VO_BORDER || cfg->win_h >= VO_BORDER || cfg->cols <= cfg->win_w || cfg->rows <= cfg->win_h)
+        return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "unsupported window / image size");
+    if (cfg->max_landmarks < 4 || cfg->max_candidates < 0 || cfg->pnp_iters < 1)
+        return vo_set_err(ctx, B200VO_E_BADARG, "bad capacities");
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    b200vo_batch* B = new b200vo_batch();
+    B->ctx = ctx; B->batch = batch; B->cfg = *cfg; B->cur = 0; B->primed = false;
+    const int levels = vo_pyr_levels(cfg->cols, cfg->rows, cfg->win_w, cfg->win_h, cfg->max_level);
+    vo_pyr_geom(cfg->rows, cfg->cols, levels, &B->geom);
+    B->kp.win_w = cfg->win_w; B->kp.win_h = cfg->win_h;
+    B->kp.max_count = (cfg->crit_type & 1) ? (cfg->crit_max_count < 0 ? 0 : cfg->crit_max_count > 100 ? 100 : cfg->crit_max_count) : 30;
+    double eps = (cfg->crit_type & 2) ? (cfg->crit_eps < 0 ? 0 : cfg->crit_eps > 10 ? 10 : cfg->crit_eps) : 0.01;
+    B->kp.eps_sq = eps * eps;
+    B->kp.min_eig_thr = (float)cfg->min_eig_thr;
+    int rc = 0;
+    for (int s = 0; s < 2 && !rc; ++s) rc = vo_reserve(ctx, B->slabs[s], B->geom.slab_bytes * batch);
+    const int cap = cfg->max_landmarks;
+    const size_t b_obj = vo_align((size_t)batch * cap * 12, 256), b_img = vo_align((size_t)batch * cap * 8, 256);
+    const size_t b_n = vo_align((size_t)batch * 4, 256), b_i = vo_align((size_t)batch * cap * 4, 256);
+    const size_t b_m = vo_align((size_t)batch * cap, 256);
+    const size_t b_ws = vo_pnp_workspace_bytes(batch, cap, cfg->pnp_iters);
+    if (!rc) rc = vo_reserve(ctx, B->work, b_obj + b_img + b_n + 2 * b_i + b_m + b_ws);
+    B->n_raw = 8 * cfg->pnp_iters + 256;
+    if (!rc) rc = vo_rng_table(ctx, B->n_raw, &B->rng);
+    if (rc) { b200vo_batch_destroy(B); return rc; }
+    uint8_t* p = (uint8_t*)B->work.p;
+    B->c_obj = (float*)p; p += b_obj;
+    B->c_img = (float*)p; p += b_img;
+    B->c_n = (int*)p; p += b_n;
+    B->c_orig = (int*)p; p += b_i;
+    B->inliers = (int*)p; p += b_i;
+    B->c_mask = p; p += b_m;
+    B->pnp_ws = p;
+    *out = B;
+    return 0;
+}
+
+extern "C" void b200vo_batch_destroy(b200vo_batch* B)
+{
+    if (!B) return;
+    cudaSetDevice(B->ctx->device);
+    cudaStreamSynchronize(B->ctx->stream);
+    for (auto& s : B->slabs) if (s.p) cudaFree(s.p);
+    for (DevBuf* d : {&B->raw, &B->pts_in, &B->outs, &B->work}) if (d->p) cudaFree(d->p);
+    if (B->prof_init) for (auto& row : B->prof_ev) for (auto& e : row) cudaEventDestroy(e);
+    delete B;
+}
+
+static int batch_upload_frames(b200vo_batch* B, const uint8_t* frames, int slab_set)
+{
+    b200vo_ctx* ctx = B->ctx;
+    const size_t fb = (size_t)B->cfg.rows * B->cfg.cols;
+    const size_t total = fb * B->batch;
+    VO_TRY(vo_reserve(ctx, B->raw, total));
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const uint8_t* src = frames;
+    if (!pinned) {   // pageable caller memory: stage through the ctx's pinned buffer
+        VO_TRY(vo_reserve_pinned(ctx, total));
+        memcpy(ctx->h_pin, frames, total);
+        src = (const uint8_t*)ctx->h_pin;
+    }
+    VO_CUDA(ctx, cudaMemcpyAsync(B->raw.p, src, total, cudaMemcpyHostToDevice, ctx->stream));
+    VO_TRY(vo_build_pyramids(ctx, (const uint8_t*)B->raw.p, fb, B->cfg.rows, B->cfg.cols, B->geom,
+                             (uint8_t*)B->slabs[slab_set].p, B->geom.slab_bytes, B->batch));
+    return 0;
+}
+
+extern "C" int b200vo_batch_prime(b200vo_batch* B, const uint8_t* frames)
+{
+    if (!B || !frames) return B200VO_E_BADARG;
+    b200vo_ctx* ctx = B->ctx;
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_TRY(batch_upload_frames(B, frames, B->cur));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B->primed = true;
+    return 0;
+}
+
+// device-resident core: everything after the new frames are in `frames_dev`
+static int batch_core(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts, const float* lm_obj,
+                      const int* n_lm, const float* cand_pts, const int* n_cand, float* lm_next,
+                      uint8_t* lm_status, float* cand_next, uint8_t* cand_status, double* pose, uint8_t* pnp_ok,
+                      uint8_t* inlier_mask, int* n_inliers)
+{
+    b200vo_ctx* ctx = B->ctx;
+    const b200vo_batch_cfg& c = B->cfg;
+    if (!B->primed) return vo_set_err(ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
+    const int nxt = B->cur ^ 1;
+    const size_t fb = (size_t)c.rows * c.cols;
+    prof_mark(B, 0);
+    VO_TRY(vo_build_pyramids(ctx, frames_dev, fb, c.rows, c.cols, B->geom, (uint8_t*)B->slabs[nxt].p,
+                             B->geom.slab_bytes, B->batch));
+    prof_mark(B, 1);
+    KltPointSet sets[2] = {{c.max_landmarks, n_lm, lm_pts, lm_next, lm_status, nullptr},
+                           {c.max_candidates, n_cand, cand_pts, cand_next, cand_status, nullptr}};
+    VO_TRY(vo_klt_launch2(ctx, B->geom, (const uint8_t*)B->slabs[B->cur].p, B->geom.slab_bytes,
+                          (const uint8_t*)B->slabs[nxt].p, B->geom.slab_bytes, B->batch, sets,
+                          c.max_candidates > 0 ? 2 : 1, 0, B->kp));
+    prof_mark(B, 2);
+    compact_tracked_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, n_lm, lm_next, lm_status, lm_obj,
+                                                              B->c_obj, B->c_img, B->c_n, B->c_orig);
+    ctx->launches++;
+    PnpArgs a{};
+    a.batch = B->batch; a.cap = c.max_landmarks; a.iters = c.pnp_iters;
+    a.obj = B->c_obj; a.img = B->c_img; a.n = B->c_n;
+    a.fx = c.K[0]; a.fy = c.K[4]; a.cx = c.K[2]; a.cy = c.K[5];
+    a.thr_sq = (float)((double)c.pnp_reproj_err * (double)c.pnp_reproj_err);
+    a.conf = c.pnp_conf;
+    a.rng_raw = B->rng; a.n_raw = B->n_raw;
+    a.inliers = B->inliers; a.mask = B->c_mask; a.pose = pose;
+    vo_pnp_carve_workspace(a, B->pnp_ws);
+    a.ok = a.ok_ws;
+    VO_TRY(vo_pnp_launch(ctx, a, true));
+    scatter_mask_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, a.ok, a.n_inliers, B->inliers, B->c_orig,
+                                                           inlier_mask, n_inliers, pnp_ok);
+    ctx->launches++;
+    prof_mark(B, 3);
+    if (B->profile && B->prof_n < B200VO_PROF_RING) B->prof_n++;
+    VO_CUDA(ctx, cudaGetLastError());
+    B->cur = nxt;
+    return 0;
+}
+
+extern "C" int b200vo_batch_step_dev(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts_dev,
+                                     const float* lm_obj_dev, const int32_t* n_lm_dev, const float* cand_pts_dev,
+                                     const int32_t* n_cand_dev, float* lm_next_dev, uint8_t* lm_status_dev,
+                                     float* cand_next_dev, uint8_t* cand_status_dev, double* pose_dev,
+                                     uint8_t* pnp_ok_dev, uint8_t* inlier_mask_dev, int32_t* n_inliers_dev)
+{
+    if (!B) return B200VO_E_BADARG;
+    VO_CUDA(B->ctx, cudaSetDevice(B->ctx->device));
+    return batch_core(B, frames_dev, lm_pts_dev, lm_obj_dev, n_lm_dev, cand_pts_dev, n_cand_dev, lm_next_dev,
+                      lm_status_dev, cand_next_dev, cand_status_dev, pose_dev, pnp_ok_dev, inlier_mask_dev,
+                      n_inliers_dev);
+}
+
+extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const float* lm_pts, const float* lm_obj,
+                                 const int32_t* n_lm, const float* cand_pts, const int32_t* n_cand, float* lm_next,
+                                 uint8_t* lm_status, float* cand_next, uint8_t* cand_status, double* pose,
+                                 uint8_t* pnp_ok, uint8_t* inlier_mask, int32_t* n_inliers)
+{
+    if (!B || !frames || !lm_pts || !lm_obj || !n_lm || !lm_next || !lm_status || !pose || !pnp_ok || !inlier_mask || !n_inliers)
+        return B200VO_E_BADARG;
+    b200vo_ctx* ctx = B->ctx;
+    const b200vo_batch_cfg& c = B->cfg;
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const int nb = B->batch, L = c.max_landmarks, Cn = c.max_candidates;
+    const size_t fb = (size_t)c.rows * c.cols, f_total = fb * nb;
+    // ---- inputs: frames (direct DMA when the caller's buffer is pinned) + one packed small block ----
+    const size_t o_lmp = 0, o_lmo = o_lmp + vo_align((size_t)nb * L * 8, 256), o_nlm = o_lmo + vo_align((size_t)nb * L * 12, 256);
+    const size_t o_cp = o_nlm + vo_align((size_t)nb * 4, 256), o_nc = o_cp + vo_align((size_t)nb * Cn * 8, 256);
+    const size_t in_bytes = o_nc + vo_align((size_t)nb * 4, 256);
+    // ---- outputs packed ----
+    const size_t q_lmn = 0, q_lms = q_lmn + vo_align((size_t)nb * L * 8, 256), q_cn = q_lms + vo_align((size_t)nb * L, 256);
+    const size_t q_cs = q_cn + vo_align((size_t)nb * Cn * 8, 256), q_pose = q_cs + vo_align((size_t)nb * Cn, 256);
+    const size_t q_ok = q_pose + vo_align((size_t)nb * 48, 256), q_mask = q_ok + vo_align((size_t)nb, 256);
+    const size_t q_ni = q_mask + vo_align((size_t)nb * L, 256), out_bytes = q_ni + vo_align((size_t)nb * 4, 256);
+    VO_TRY(vo_reserve(ctx, B->raw, f_total));
+    VO_TRY(vo_reserve(ctx, B->pts_in, in_bytes));
+    VO_TRY(vo_reserve(ctx, B->outs, out_bytes));
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    VO_TRY(vo_reserve_pinned(ctx, (pinned ? 0 : f_total) + in_bytes + out_bytes));
+    uint8_t* hp = (uint8_t*)ctx->h_pin;
+    const uint8_t* fsrc = frames;
+    if (!pinned) { memcpy(hp, frames, f_total); fsrc = hp; hp += f_total; }
+    VO_CUDA(ctx, cudaMemcpyAsync(B->raw.p, fsrc, f_total, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(hp + o_lmp, lm_pts, (size_t)nb * L * 8);
+    memcpy(hp + o_lmo, lm_obj, (size_t)nb * L * 12);
+    memcpy(hp + o_nlm, n_lm, (size_t)nb * 4);
+    if (Cn > 0 && cand_pts && n_cand) {
+        memcpy(hp + o_cp, cand_pts, (size_t)nb * Cn * 8);
+        memcpy(hp + o_nc, n_cand, (size_t)nb * 4);
+    } else {
+        memset(hp + o_nc, 0, (size_t)nb * 4);
+    }
+    uint8_t* di = (uint8_t*)B->pts_in.p;
+    VO_CUDA(ctx, cudaMemcpyAsync(di, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* dq = (uint8_t*)B->outs.p;
+    VO_TRY(batch_core(B, (const uint8_t*)B->raw.p, (const float*)(di + o_lmp), (const float*)(di + o_lmo),
+                      (const int*)(di + o_nlm), (const float*)(di + o_cp), (const int*)(di + o_nc),
+                      (float*)(dq + q_lmn), dq + q_lms, (float*)(dq + q_cn), dq + q_cs, (double*)(dq + q_pose),
+                      dq + q_ok, dq + q_mask, (int*)(dq + q_ni)));
+    uint8_t* ho = hp + in_bytes;
+    VO_CUDA(ctx, cudaMemcpyAsync(ho, dq, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    memcpy(lm_next, ho + q_lmn, (size_t)nb * L * 8);
+    memcpy(lm_status, ho + q_lms, (size_t)nb * L);
+    if (Cn > 0 && cand_next && cand_status) {
+        memcpy(cand_next, ho + q_cn, (size_t)nb * Cn * 8);
+        memcpy(cand_status, ho + q_cs, (size_t)nb * Cn);
+    }
+    memcpy(pose, ho + q_pose, (size_t)nb * 48);
+    memcpy(pnp_ok, ho + q_ok, (size_t)nb);
+    memcpy(inlier_mask, ho + q_mask, (size_t)nb * L);
+    memcpy(n_inliers, ho + q_ni, (size_t)nb * 4);
+    return 0;
+}
+
+extern "C" int b200vo_batch_profile(b200vo_batch* B, int enable)
+{
+    if (!B) return B200VO_E_BADARG;
+    cudaSetDevice(B->ctx->device);
+    if (enable && !B->prof_init) {
+        for (auto& row : B->prof_ev) for (auto& e : row) cudaEventCreate(&e);
+        B->prof_init = true;
+    }
+    B->profile = enable != 0;
+    B->prof_n = 0;
+    return 0;
+}
+
+extern "C" int b200vo_batch_profile_read(b200vo_batch* B, float* stage_ms, int* n_steps)
+{
+    if (!B || !stage_ms || !n_steps) return B200VO_E_BADARG;
+    cudaSetDevice(B->ctx->device);
+    cudaStreamSynchronize(B->ctx->stream);
+    for (int s = 0; s < B200VO_PROF_STAGES; ++s) stage_ms[s] = 0.f;
+    for (int i = 0; i < B->prof_n; ++i)
+        for (int s = 0; s < B200VO_PROF_STAGES; ++s) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, B->prof_ev[i][s], B->prof_ev[i][s + 1]);
+            stage_ms[s] += ms;
+        }
+    *n_steps = B->prof_n;
+    return 0;
+}
+
+extern "C" void* b200vo_host_alloc(b200vo_ctx* ctx, size_t bytes)
+{
+    if (!ctx || bytes == 0) return nullptr;
+    cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void b200vo_host_free(b200vo_ctx* ctx, void* p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(p);
+}

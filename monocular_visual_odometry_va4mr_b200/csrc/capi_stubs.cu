@@ -5,8 +5,3 @@
 extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t*, int, int, size_t, int, double, double, int, float*, int*) { STUB(ctx); }
 extern "C" int b200vo_knn2_ratio(b200vo_ctx* ctx, const float*, int, const float*, int, int, double, int32_t*, float*, uint8_t*) { STUB(ctx); }
 extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float*, const float*, int, const double*, double, double, int, double*, uint8_t*, int*) { STUB(ctx); }
-extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int, const b200vo_batch_cfg*, b200vo_batch**) { STUB(ctx); }
-extern "C" void b200vo_batch_destroy(b200vo_batch*) {}
-extern "C" int b200vo_batch_prime(b200vo_batch*, const uint8_t*) { return B200VO_E_UNSUPPORTED; }
-extern "C" int b200vo_batch_step(b200vo_batch*, const uint8_t*, const float*, const float*, const int32_t*, const float*, const int32_t*, float*, uint8_t*, float*, uint8_t*, double*, uint8_t*, uint8_t*, int32_t*) { return B200VO_E_UNSUPPORTED; }
-extern "C" int b200vo_batch_step_dev(b200vo_batch*, const uint8_t*, const float*, const float*, const int32_t*, const float*, const int32_t*, float*, uint8_t*, float*, uint8_t*, double*, uint8_t*, uint8_t*, int32_t*) { return B200VO_E_UNSUPPORTED; }

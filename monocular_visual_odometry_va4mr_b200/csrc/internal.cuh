@@ -96,6 +96,17 @@ int vo_build_pyramids(b200vo_ctx* ctx, const uint8_t* d_raw, size_t raw_stride, 
                       const PyrGeom& g, uint8_t* d_slab, size_t slab_stride, int batch);
 
 // ---- klt.cu ----
+struct KltPointSet {
+    int cap;            // slots per sequence
+    const int* n;       // [batch] live points per sequence (device) or nullptr -> n_fixed
+    const float* pts;   // [batch][cap][2]
+    float* out;         // [batch][cap][2]
+    uint8_t* status;    // [batch][cap]
+    float* err;         // [batch][cap] or nullptr
+};
+int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,
+                   const uint8_t* d_next_slab, size_t next_stride, int batch, const KltPointSet* sets, int n_sets,
+                   int n_fixed, const KltParams& kp);
 // Tracks points of `batch` independent frame pairs.  pts/next/status/err are
 // [batch][cap] arrays; n_pts (device) gives the live count per pair (or nullptr -> n_fixed).
 int vo_klt_launch(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,

@@ -23,12 +23,14 @@ struct KltArgs {
     unsigned long long off[VO_MAX_LEVELS];
     int w[VO_MAX_LEVELS], h[VO_MAX_LEVELS], pitch[VO_MAX_LEVELS];
     int levels;
-    int batch, cap, n_fixed;
-    const int* n_pts;
-    const float* pts;
-    float* out;
-    uint8_t* status;
-    float* err;
+    int batch, n_fixed;
+    // up to two point sets per sequence (landmark keypoints, candidate keypoints): [batch][cap[s]]
+    int cap[2];
+    const int* n_pts[2];
+    const float* pts[2];
+    float* out[2];
+    uint8_t* status[2];
+    float* err[2];
     int win_w, win_h, max_count;
     double eps_sq;
     float min_eig_thr;
@@ -70,10 +72,13 @@ klt_kernel(const KltArgs a)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * KLT_WARPS + warp;
-    const int seq = (int)(gw / a.cap);
-    const int pi = (int)(gw - (long long)seq * a.cap);
+    const int cap_all = a.cap[0] + a.cap[1];
+    const int seq = (int)(gw / cap_all);
+    int pi = (int)(gw - (long long)seq * cap_all);
     if (seq >= a.batch) return;
-    const int n_here = a.n_pts ? a.n_pts[seq] : a.n_fixed;
+    const int seg = pi >= a.cap[0] ? 1 : 0;
+    pi -= seg ? a.cap[0] : 0;
+    const int n_here = a.n_pts[seg] ? a.n_pts[seg][seq] : a.n_fixed;
     if (pi >= n_here) return;
 
     const int ww = WW ? WW : a.win_w;
@@ -88,8 +93,8 @@ klt_kernel(const KltArgs a)
 
     const uint8_t* prev = a.prev + (size_t)seq * a.prev_stride;
     const uint8_t* next = a.next + (size_t)seq * a.next_stride;
-    const size_t pidx = (size_t)seq * a.cap + pi;
-    const float px0 = a.pts[2 * pidx], py0 = a.pts[2 * pidx + 1];
+    const size_t pidx = (size_t)seq * a.cap[seg] + pi;
+    const float px0 = a.pts[seg][2 * pidx], py0 = a.pts[seg][2 * pidx + 1];
     const float hwx = (ww - 1) * 0.5f, hwy = (wh - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
 
@@ -243,19 +248,18 @@ klt_kernel(const KltArgs a)
         }
     }
     if (lane == 0) {
-        a.out[2 * pidx] = outx;
-        a.out[2 * pidx + 1] = outy;
-        a.status[pidx] = (uint8_t)st;
-        a.err[pidx] = e;
+        a.out[seg][2 * pidx] = outx;
+        a.out[seg][2 * pidx + 1] = outy;
+        a.status[seg][pidx] = (uint8_t)st;
+        if (a.err[seg]) a.err[seg][pidx] = e;
     }
 }
 
-int vo_klt_launch(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,
-                  const uint8_t* d_next_slab, size_t next_stride, int batch, int cap,
-                  const int* d_n_pts, int n_fixed, const float* d_pts, float* d_next,
-                  uint8_t* d_status, float* d_err, const KltParams& kp)
+int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,
+                   const uint8_t* d_next_slab, size_t next_stride, int batch, const KltPointSet* sets, int n_sets,
+                   int n_fixed, const KltParams& kp)
 {
-    if (batch <= 0 || cap <= 0) return 0;
+    if (batch <= 0 || n_sets <= 0) return 0;
     KltArgs a{};
     a.prev = d_prev_slab; a.next = d_next_slab;
     a.prev_stride = prev_stride; a.next_stride = next_stride;
@@ -263,8 +267,17 @@ int vo_klt_launch(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab,
     for (int l = 0; l < g.levels; ++l) {
         a.off[l] = g.off[l]; a.w[l] = g.w[l]; a.h[l] = g.h[l]; a.pitch[l] = g.pitch[l];
     }
-    a.batch = batch; a.cap = cap; a.n_fixed = n_fixed; a.n_pts = d_n_pts;
-    a.pts = d_pts; a.out = d_next; a.status = d_status; a.err = d_err;
+    a.batch = batch; a.n_fixed = n_fixed;
+    for (int s = 0; s < 2; ++s) {
+        const bool on = s < n_sets;
+        a.cap[s] = on ? sets[s].cap : 0;
+        a.n_pts[s] = on ? sets[s].n : nullptr;
+        a.pts[s] = on ? sets[s].pts : nullptr;
+        a.out[s] = on ? sets[s].out : nullptr;
+        a.status[s] = on ? sets[s].status : nullptr;
+        a.err[s] = on ? sets[s].err : nullptr;
+    }
+    if (a.cap[0] + a.cap[1] <= 0) return 0;
     a.win_w = kp.win_w; a.win_h = kp.win_h; a.max_count = kp.max_count;
     a.eps_sq = kp.eps_sq; a.min_eig_thr = kp.min_eig_thr;
     a.patch_stride = (int)vo_align((size_t)kp.win_w + 3 + 3, 4);
@@ -274,7 +287,7 @@ int vo_klt_launch(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab,
     a.smem_di = (int)vo_align((size_t)kp.win_w * kp.win_h * 4, 16);
     a.smem_per_warp = a.smem_patch + a.smem_der + a.smem_iwin + a.smem_di;
     const size_t smem = (size_t)a.smem_per_warp * KLT_WARPS;
-    const long long total_warps = (long long)batch * cap;
+    const long long total_warps = (long long)batch * (a.cap[0] + a.cap[1]);
     const unsigned grid = (unsigned)((total_warps + KLT_WARPS - 1) / KLT_WARPS);
     void (*kern)(const KltArgs) = nullptr;
     if (kp.win_w == 21 && kp.win_h == 21) kern = klt_kernel<21, 21>;
@@ -286,4 +299,13 @@ int vo_klt_launch(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab,
     ctx->launches++;
     VO_CUDA(ctx, cudaGetLastError());
     return 0;
+}
+
+int vo_klt_launch(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,
+                  const uint8_t* d_next_slab, size_t next_stride, int batch, int cap,
+                  const int* d_n_pts, int n_fixed, const float* d_pts, float* d_next,
+                  uint8_t* d_status, float* d_err, const KltParams& kp)
+{
+    KltPointSet s{cap, d_n_pts, d_pts, d_next, d_status, d_err};
+    return vo_klt_launch2(ctx, g, d_prev_slab, prev_stride, d_next_slab, next_stride, batch, &s, 1, n_fixed, kp);
 }

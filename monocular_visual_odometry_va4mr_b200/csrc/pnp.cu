@@ -597,7 +597,7 @@ size_t vo_pnp_workspace_bytes(int batch, int cap, int iters)
     b += vo_align((size_t)batch * iters * 12 * sizeof(double), 256);   // hyp
     b += vo_align((size_t)batch * iters * 3 * sizeof(double), 256);    // hyp_rvec
     b += 2 * vo_align((size_t)batch * iters * sizeof(int), 256);       // hyp_ok, counts
-    b += 4 * vo_align((size_t)batch * sizeof(int), 256);               // winner, iters_run, n_inliers, flags
+    b += 5 * vo_align((size_t)batch * sizeof(int), 256);               // winner, iters_run, n_inliers, flags, ok_ws
     return b;
 }
 
@@ -614,6 +614,7 @@ void vo_pnp_carve_workspace(PnpArgs& a, void* ws)
     a.iters_run = (int*)take((size_t)a.batch * sizeof(int));
     a.n_inliers = (int*)take((size_t)a.batch * sizeof(int));
     a.flags = (int*)take((size_t)a.batch * sizeof(int));
+    a.ok_ws = (uint8_t*)take((size_t)a.batch * sizeof(int));
 }
 
 int vo_pnp_launch(b200vo_ctx* ctx, const PnpArgs& a, bool gen_samples)

@@ -25,6 +25,7 @@ struct PnpArgs {
     int* iters_run;         // [batch]
     int* n_inliers;         // [batch]
     int* flags;             // [batch] bit0: raw RNG table exhausted
+    uint8_t* ok_ws;         // [batch] spare per-sequence success flags (callers may point `ok` here)
     // outputs
     int* inliers;           // [batch][cap] ascending indices
     uint8_t* mask;          // [batch][cap]

@@ -1,0 +1,106 @@
+"""Batched KLT + PnP step (b200vo_batch_step) against the per-call path, the oracle and live cv2."""
+import numpy as np
+import pytest
+
+from monocular_visual_odometry_va4mr_b200 import cv2_compat, workload
+from monocular_visual_odometry_va4mr_b200.batch import SequenceBatch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def wl():
+    return workload.TrackWorkload("kitti", batch=5, n_frames=3, n_landmarks=300, n_candidates=200, n_distinct=2,
+                                  seed=1, width=640, height=240, cap_landmarks=320, cap_candidates=256)
+
+
+def _run_steps(wl, n_steps, opts, pinned=False):
+    sb = SequenceBatch(wl.batch, wl.h, wl.w, wl.K, win=opts["win"], max_level=opts["max_level"], criteria=opts["criteria"],
+                       pnp_iters=opts["pnp_iters"], pnp_reproj_err=opts["pnp_err"], pnp_conf=opts["pnp_conf"],
+                       max_landmarks=wl.L, max_candidates=wl.Cn)
+    order = workload.frame_order(wl.F, n_steps)
+    frames = wl.frames
+    if pinned:
+        frames = sb.pinned_frames(wl.F)
+        frames[:] = wl.frames
+    sb.prime(frames[order[0]])
+    outs = []
+    for t in range(n_steps):
+        f, g = order[t], order[t + 1]
+        o = sb.step(frames[g], wl.lm_pts[f], wl.lm_obj[f], wl.n_lm[f], wl.cand_pts[f], wl.n_cand[f])
+        outs.append({k: v.copy() for k, v in o.items()})
+    sb.close()
+    return order, outs
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_batch_equals_per_call_path(wl, pinned):
+    opts = workload.REFERENCE_OPTIONS["kitti"]
+    order, outs = _run_steps(wl, 4, opts, pinned)
+    for t, o in enumerate(outs):
+        f, g = order[t], order[t + 1]
+        for s in range(wl.batch):
+            nl, nc = int(wl.n_lm[f, s]), int(wl.n_cand[f, s])
+            p, st, _ = cv2_compat.calcOpticalFlowPyrLK(wl.frames[f, s], wl.frames[g, s], wl.lm_pts[f, s, :nl], None,
+                                                       winSize=opts["win"], maxLevel=opts["max_level"], criteria=opts["criteria"])
+            assert np.array_equal(o["lm_status"][s, :nl], st.ravel())
+            assert np.array_equal(o["lm_next"][s, :nl], p)
+            pc, stc, _ = cv2_compat.calcOpticalFlowPyrLK(wl.frames[f, s], wl.frames[g, s], wl.cand_pts[f, s, :nc], None,
+                                                         winSize=opts["win"], maxLevel=opts["max_level"], criteria=opts["criteria"])
+            assert np.array_equal(o["cand_status"][s, :nc], stc.ravel())
+            assert np.array_equal(o["cand_next"][s, :nc], pc)
+            keep = st.ravel() == 1
+            ok, rv, tv, inl = cv2_compat.solvePnPRansac(wl.lm_obj[f, s, :nl][keep], p[keep], wl.K, np.zeros(4),
+                                                        flags=cv2_compat.SOLVEPNP_P3P, confidence=opts["pnp_conf"],
+                                                        reprojectionError=opts["pnp_err"], iterationsCount=opts["pnp_iters"])
+            assert bool(o["pnp_ok"][s]) == ok
+            mask = np.zeros(wl.L, np.uint8)
+            mask[np.flatnonzero(keep)[inl.ravel()]] = 1
+            assert np.array_equal(o["inlier_mask"][s], mask)
+            assert int(o["n_inliers"][s]) == len(inl)
+            assert np.array_equal(o["pose"][s], np.concatenate([rv.ravel(), tv.ravel()]))
+
+
+def test_batch_vs_oracle_and_truth(wl):
+    import oracle
+    opts = workload.REFERENCE_OPTIONS["kitti"]
+    order, outs = _run_steps(wl, 2, opts)
+    for t, o in enumerate(outs):
+        f, g = order[t], order[t + 1]
+        for s in range(wl.batch):
+            nl = int(wl.n_lm[f, s])
+            rp, rst, _ = oracle.calc_optical_flow_pyr_lk(wl.frames[f, s], wl.frames[g, s], wl.lm_pts[f, s, :nl],
+                                                         opts["win"], opts["max_level"], opts["criteria"])
+            assert np.array_equal(o["lm_status"][s, :nl], rst.ravel())
+            keep = rst.ravel() == 1
+            assert np.abs(o["lm_next"][s, :nl] - rp)[keep].max() <= 0.05
+            ok, rv, tv, inl, _ = oracle.solve_pnp_ransac_p3p(wl.lm_obj[f, s, :nl][keep], rp[keep], wl.K, opts["pnp_iters"],
+                                                             opts["pnp_err"], opts["pnp_conf"])
+            assert ok and o["pnp_ok"][s]
+            assert np.array_equal(np.flatnonzero(o["inlier_mask"][s]), np.flatnonzero(keep)[inl.ravel()])
+            assert np.abs(o["pose"][s] - np.concatenate([rv.ravel(), tv.ravel()])).max() < 1e-6
+            # and the recovered pose is the rendered camera (synthetic ground truth), loosely
+            R, tt = wl.true_pose(s, g)
+            assert np.abs(oracle.rodrigues_to_R(o["pose"][s, :3]) - R).max() < 0.02
+            assert np.abs(o["pose"][s, 3:] - tt).max() < 0.3
+
+
+def test_batch_live_cv2(wl):
+    cv2 = pytest.importorskip("cv2")
+    opts = workload.REFERENCE_OPTIONS["kitti"]
+    order, outs = _run_steps(wl, 2, opts)
+    for t, o in enumerate(outs):
+        f, g = order[t], order[t + 1]
+        for s in range(wl.batch):
+            nl = int(wl.n_lm[f, s])
+            p, st, _ = cv2.calcOpticalFlowPyrLK(wl.frames[f, s], wl.frames[g, s], wl.lm_pts[f, s, :nl], None,
+                                                winSize=opts["win"], maxLevel=opts["max_level"], criteria=opts["criteria"])
+            assert np.array_equal(o["lm_status"][s, :nl], st.ravel())
+            keep = st.ravel() == 1
+            d = np.abs(o["lm_next"][s, :nl] - p)[keep].max(axis=1)
+            assert (d <= 0.05).mean() >= 0.99
+            if d.max() == 0:   # identical tracked positions -> PnP must agree exactly on the inlier set
+                ok, rv, tv, inl = cv2.solvePnPRansac(wl.lm_obj[f, s, :nl][keep], p[keep], wl.K, np.zeros(4),
+                                                     flags=cv2.SOLVEPNP_P3P, confidence=opts["pnp_conf"],
+                                                     reprojectionError=opts["pnp_err"], iterationsCount=opts["pnp_iters"])
+                assert np.array_equal(np.flatnonzero(o["inlier_mask"][s]), np.flatnonzero(keep)[inl.ravel()])
