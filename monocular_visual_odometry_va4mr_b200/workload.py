@@ -16,9 +16,12 @@ from . import synth
 
 # the reference's per-dataset options that reach the hot path (main.py:20-44, 50-74, 80-104)
 REFERENCE_OPTIONS = {
-    "kitti": dict(win=(15, 15), max_level=5, criteria=(3, 50, 0.01), pnp_err=8.0, pnp_iters=500, pnp_conf=0.99),
-    "malaga": dict(win=(15, 15), max_level=10, criteria=(3, 50, 0.01), pnp_err=5.0, pnp_iters=500, pnp_conf=0.99),
-    "parking": dict(win=(15, 15), max_level=10, criteria=(3, 50, 0.02), pnp_err=5.0, pnp_iters=500, pnp_conf=0.99),
+    "kitti": dict(win=(15, 15), max_level=5, criteria=(3, 50, 0.01), pnp_err=8.0, pnp_iters=500, pnp_conf=0.99,
+                  min_dist=1.0, max_dist=150.0),
+    "malaga": dict(win=(15, 15), max_level=10, criteria=(3, 50, 0.01), pnp_err=5.0, pnp_iters=500, pnp_conf=0.99,
+                   min_dist=0.0, max_dist=100.0),
+    "parking": dict(win=(15, 15), max_level=10, criteria=(3, 50, 0.02), pnp_err=5.0, pnp_iters=500, pnp_conf=0.99,
+                    min_dist=1.0, max_dist=50.0),
 }
 
 
@@ -62,6 +65,13 @@ class TrackWorkload:
                 pts = pool[d, f][rng.permutation(len(pool[d, f]))]
                 nl = min(self.L, n_landmarks - (s % 5) * 7)          # ragged live counts
                 nc = min(self.Cn, n_candidates - (s % 3) * 11) if self.Cn else 0
+                # the reference only keeps landmarks within [min_dist, max_dist] of the camera
+                # (main.py:22-23 ...; VisualOdometryPipeLine.py:168): landmarks come from that depth band
+                zi = sq["depth"][f][np.clip(np.rint(pts[:, 1]).astype(int), 0, self.h - 1),
+                                    np.clip(np.rint(pts[:, 0]).astype(int), 0, self.w - 1)]
+                near = (zi > REFERENCE_OPTIONS[shape]["min_dist"]) & (zi < 0.6 * REFERENCE_OPTIONS[shape]["max_dist"])
+                pts = np.concatenate([pts[near], pts[~near]])
+                nl = min(nl, int(near.sum()))
                 lp = pts[:nl]
                 # landmark = back-projection of the keypoint displaced by the triangulation noise
                 X = synth.backproject(self.K, sq["R_cw"][f], sq["c"][f],
