@@ -1,0 +1,332 @@
+// Shi-Tomasi corner detection (replaces cv2.goodFeaturesToTrack at reference
+// VisualOdometryPipeLine.py:256; spec SURVEY.md A.4 and the arithmetic pinned in
+// oracle/gftt_oracle.c).
+//
+// The float32 operation order reproduces cv2 4.13's min-eigenvalue map bit for bit (fused
+// multiply-adds exactly where its AVX2 filters fuse, box sums as a running column sum in
+// double), because the ordered corner list is decided by last-bit ties between symmetric
+// corners.  Pipeline:
+//   gftt_cov_kernel        Sobel (scaled) -> Dx^2, DxDy, Dy^2             (1 thread / pixel)
+//   gftt_box_eig_kernel    3x3 box as running column sums in double, eig  (1 thread / column)
+//   gftt_candidates_kernel threshold at q*max, 3x3 non-maximum test, compaction of 64-bit keys
+//   gftt_rank_kernel       order by (value desc, address desc): rank by counting (n <= 32768)
+//   gftt_bitonic_*         same order for larger candidate sets
+//   gftt_select_kernel     greedy min-distance suppression on a cell grid, warp-speculative:
+//                          32 candidates tested against the accepted set at once, survivors
+//                          resolved in order -- result identical to the sequential loop.
+#include "internal.cuh"
+
+__device__ __forceinline__ int refl101(int p, int len)
+{
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+// img: bordered level-0 (REFLECT_101 border materialised), base -> pixel (0,0)
+__global__ void __launch_bounds__(256)
+gftt_cov_kernel(const uint8_t* __restrict__ img, int pitch, int w, int h, float k0, float k1, float* __restrict__ cov)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* r0 = img + (long long)(y - 1) * pitch + x;
+    const uint8_t* r1 = r0 + pitch;
+    const uint8_t* r2 = r1 + pitch;
+    const int a0 = r0[-1], a1 = r0[0], a2 = r0[1];
+    const int b0 = r1[-1], b2 = r1[1];
+    const int c0 = r2[-1], c1 = r2[0], c2 = r2[1];
+    // Dx: symmetric column filter over exact row differences, fused as cv2's AVX2 path
+    const int s0 = a2 - a0, s1 = b2 - b0, s2 = c2 - c0;
+    const float dx = __fmaf_rn((float)(s0 + s2), k0, __fmul_rn((float)s1, k1));
+    // Dy: smoothed rows (fused in the vectorised body, unfused in the scalar tail), then r[y+1]-r[y-1]
+    float rt, rb;
+    if (x < (w & ~31)) {
+        rt = __fmaf_rn(k0, (float)a2, __fmaf_rn(k1, (float)a1, __fmul_rn(k0, (float)a0)));
+        rb = __fmaf_rn(k0, (float)c2, __fmaf_rn(k1, (float)c1, __fmul_rn(k0, (float)c0)));
+    } else {
+        rt = __fadd_rn(__fadd_rn(__fmul_rn(k0, (float)a0), __fmul_rn(k1, (float)a1)), __fmul_rn(k0, (float)a2));
+        rb = __fadd_rn(__fadd_rn(__fmul_rn(k0, (float)c0), __fmul_rn(k1, (float)c1)), __fmul_rn(k0, (float)c2));
+    }
+    const float dy = __fsub_rn(rb, rt);
+    float* c = cov + 3 * ((size_t)y * w + x);
+    c[0] = __fmul_rn(dx, dx); c[1] = __fmul_rn(dx, dy); c[2] = __fmul_rn(dy, dy);
+}
+
+// one thread per column: running column sum (double) of the double row sums, then the eigenvalue
+__global__ void __launch_bounds__(128)
+gftt_box_eig_kernel(const float* __restrict__ cov, int w, int h, float* __restrict__ eig, int* __restrict__ max_bits)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    float vmax = 0.f;
+    if (x < w) {
+        const int xm = refl101(x - 1, w), xp = refl101(x + 1, w);
+        auto rowsum = [&](int yy, double* o) {
+            const float* r = cov + 3 * (size_t)refl101(yy, h) * w;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                o[ch] = __dadd_rn(__dadd_rn((double)r[3 * xm + ch], (double)r[3 * x + ch]), (double)r[3 * xp + ch]);
+        };
+        double SUM[3] = {0., 0., 0.}, prev1[3], prev0[3], cur[3];
+        rowsum(-1, prev1);   // leaving row for y = 0
+        rowsum(0, prev0);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) SUM[ch] = __dadd_rn(__dadd_rn(0., prev1[ch]), prev0[ch]);
+        for (int y = 0; y < h; ++y) {
+            rowsum(y + 1, cur);
+            float bx[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const double s0 = __dadd_rn(SUM[ch], cur[ch]);
+                bx[ch] = (float)s0;
+                SUM[ch] = __dsub_rn(s0, prev1[ch]);
+                prev1[ch] = prev0[ch]; prev0[ch] = cur[ch];
+            }
+            const float a = __fmul_rn(bx[0], 0.5f), b = bx[1], c = __fmul_rn(bx[2], 0.5f);
+            const float t = __fsub_rn(a, c);
+            const float v = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+            eig[(size_t)y * w + x] = v;
+            vmax = fmaxf(vmax, v);
+        }
+    }
+    // eig >= 0 up to rounding; negative values never win the max (cv2's max would be >= 0 too)
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 16));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 8));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 4));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 2));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_bits, __float_as_int(vmax));
+}
+
+__global__ void __launch_bounds__(256)
+gftt_candidates_kernel(const float* __restrict__ eig, int w, int h, const int* __restrict__ max_bits, double quality,
+                       unsigned long long* __restrict__ keys, int* __restrict__ n_keys, int cap)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    bool is_c = false;
+    float v = 0.f;
+    if (x < w - 1 && y < h - 1) {
+        const float thr = (float)((double)__int_as_float(*max_bits) * quality);
+        const float* p = eig + (size_t)y * w + x;
+        v = p[0];
+        if (v > thr) {
+            is_c = !(p[-w - 1] > v || p[-w] > v || p[-w + 1] > v || p[-1] > v || p[1] > v || p[w - 1] > v || p[w] > v || p[w + 1] > v);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, is_c);
+    if (!m) return;
+    const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(n_keys, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (is_c) {
+        const int pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < cap) keys[pos] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+    }
+}
+
+// descending order of the 64-bit keys = (value desc, address desc); keys are unique
+__global__ void __launch_bounds__(256)
+gftt_rank_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ n_keys, int cap,
+                 unsigned long long* __restrict__ sorted)
+{
+    __shared__ unsigned long long tile[1024];
+    const int n = min(*n_keys, cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= n) return;
+    const unsigned long long mine = i < n ? keys[i] : 0ull;
+    int rank = 0;
+    for (int t0 = 0; t0 < n; t0 += 1024) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) tile[k] = (t0 + k < n) ? keys[t0 + k] : 0ull;
+        __syncthreads();
+        const int lim = min(1024, n - t0);
+#pragma unroll 8
+        for (int k = 0; k < lim; ++k) rank += tile[k] > mine;
+    }
+    if (i < n) sorted[rank] = mine;
+}
+
+// bitonic sort (descending) in global memory for large candidate sets; n_pad = power of two
+__global__ void gftt_bitonic_pad_kernel(unsigned long long* keys, const int* n_keys, int cap, int n_pad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(*n_keys, cap);
+    if (i < n_pad && i >= n) keys[i] = 0ull;
+}
+__global__ void gftt_bitonic_step_kernel(unsigned long long* keys, int j, int k, int n_pad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    const int l = i ^ j;
+    if (l > i) {
+        const unsigned long long a = keys[i], b = keys[l];
+        const bool desc = (i & k) == 0;
+        if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[l] = a; }
+    }
+}
+
+#define GFTT_CELL_CAP 8
+// single warp; grid cells hold accepted corners (x | y << 16)
+__global__ void __launch_bounds__(32)
+gftt_select_kernel(const unsigned long long* __restrict__ sorted, const int* __restrict__ n_keys, int cap, int w, int h,
+                   int max_corners, double min_dist, int cell, int gw, int gh, int* __restrict__ cell_cnt,
+                   int* __restrict__ cell_pts, float* __restrict__ corners, int* __restrict__ n_out)
+{
+    const int lane = threadIdx.x;
+    const int n = min(*n_keys, cap);
+    const double md2 = min_dist * min_dist;
+    int n_acc = 0;
+    const int limit = max_corners > 0 ? max_corners : 0x7fffffff;
+    if (min_dist < 1) {
+        const int m = min(n, limit);
+        for (int i = lane; i < m; i += 32) {
+            const int idx = (int)(sorted[i] & 0xffffffffu);
+            corners[2 * i] = (float)(idx % w); corners[2 * i + 1] = (float)(idx / w);
+        }
+        if (lane == 0) *n_out = m;
+        return;
+    }
+    for (int i0 = 0; i0 < n && n_acc < limit; i0 += 32) {
+        const int i = i0 + lane;
+        int x = 0, y = 0;
+        bool alive = i < n;
+        if (alive) {
+            const int idx = (int)(sorted[i] & 0xffffffffu);
+            y = idx / w; x = idx - y * w;
+            const int xc = x / cell, yc = y / cell;
+            const int x1 = max(0, xc - 1), y1 = max(0, yc - 1), x2 = min(gw - 1, xc + 1), y2 = min(gh - 1, yc + 1);
+            for (int yy = y1; yy <= y2 && alive; ++yy)
+                for (int xx = x1; xx <= x2 && alive; ++xx) {
+                    const int c = yy * gw + xx;
+                    const int cnt = __ldcg(cell_cnt + c);
+                    for (int j = 0; j < cnt; ++j) {
+                        const int p = __ldcg(cell_pts + c * GFTT_CELL_CAP + j);
+                        const float dx = (float)(x - (p & 0xffff)), dy = (float)(y - (p >> 16));
+                        if ((double)(dx * dx + dy * dy) < md2) { alive = false; break; }
+                    }
+                }
+        }
+        // survivors of this chunk: accept in order, each acceptance kills later survivors within min_dist
+        unsigned surv = __ballot_sync(0xffffffffu, alive);
+        while (surv && n_acc < limit) {
+            const int f = __ffs(surv) - 1;
+            const int fx = __shfl_sync(0xffffffffu, x, f), fy = __shfl_sync(0xffffffffu, y, f);
+            if (lane == f) {
+                const int c = (y / cell) * gw + (x / cell);
+                const int cnt = cell_cnt[c];
+                if (cnt < GFTT_CELL_CAP) { cell_pts[c * GFTT_CELL_CAP + cnt] = x | (y << 16); cell_cnt[c] = cnt + 1; }
+                corners[2 * n_acc] = (float)x; corners[2 * n_acc + 1] = (float)y;
+                alive = false;
+            }
+            ++n_acc;
+            if (alive) {
+                const float dx = (float)(x - fx), dy = (float)(y - fy);
+                if ((double)(dx * dx + dy * dy) < md2) alive = false;
+            }
+            surv = __ballot_sync(0xffffffffu, alive);
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+    if (lane == 0) *n_out = n_acc;
+}
+
+extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img, int rows, int cols, size_t step,
+                                             int max_corners, double quality, double min_dist, int block_size,
+                                             float* corners_xy, int* n_out)
+{
+    if (!ctx || !img || !corners_xy || !n_out) return B200VO_E_BADARG;
+    *n_out = 0;
+    if (!(quality > 0) || min_dist < 0 || max_corners < 0)   // cv2: featureselect.cpp CV_Assert
+        return vo_set_err(ctx, B200VO_E_BADARG, "qualityLevel > 0 && minDistance >= 0 && maxCorners >= 0");
+    if (block_size != 3) return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "blockSize != 3 not implemented (the reference uses 3)");
+    if (rows < 3 || cols < 3 || cols >= 65536 || rows >= 32768) return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "image size");
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const int w = cols, h = rows;
+    const size_t npx = (size_t)w * h;
+    // bordered level 0 in the internal slot
+    FrameSlot& fs = ctx->slots[B200VO_MAX_SLOTS + 1];
+    PyrGeom g;
+    vo_pyr_geom(rows, cols, 1, &g);
+    VO_TRY(vo_reserve(ctx, fs.slab, g.slab_bytes));
+    fs.valid = false;
+    VO_TRY(vo_reserve(ctx, ctx->d_stage_img[1], npx));
+    VO_TRY(vo_reserve_pinned(ctx, vo_align(npx, 256) + 4096));
+    uint8_t* hp = (uint8_t*)ctx->h_pin;
+    if (step == (size_t)cols) memcpy(hp, img, npx);
+    else for (int y = 0; y < rows; ++y) memcpy(hp + (size_t)y * cols, img + (size_t)y * step, (size_t)cols);
+    VO_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_img[1].p, hp, npx, cudaMemcpyHostToDevice, ctx->stream));
+    VO_TRY(vo_build_pyramids(ctx, (const uint8_t*)ctx->d_stage_img[1].p, npx, rows, cols, g, (uint8_t*)fs.slab.p, g.slab_bytes, 1));
+    const uint8_t* d_img = (const uint8_t*)fs.slab.p + g.off[0];
+    // scratch: cov | eig | keys | sorted | cells | small
+    const int cell = min_dist >= 1 ? (int)llrint(min_dist) : 1;
+    const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+    const int cap = (int)npx;
+    int n_pad = 1;
+    while (n_pad < cap) n_pad <<= 1;
+    const size_t b_cov = vo_align(npx * 12, 256), b_eig = vo_align(npx * 4, 256), b_keys = vo_align((size_t)n_pad * 8, 256);
+    const size_t b_cnt = vo_align((size_t)gw * gh * 4, 256), b_pts = vo_align((size_t)gw * gh * GFTT_CELL_CAP * 4, 256);
+    const size_t out_cap = max_corners > 0 ? (size_t)max_corners : npx;
+    const size_t b_out = vo_align(out_cap * 8, 256), b_small = 256;
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[2], b_cov + b_eig + 2 * b_keys + b_cnt + b_pts + b_out + b_small));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[2].p;
+    float* d_cov = (float*)d; d += b_cov;
+    float* d_eig = (float*)d; d += b_eig;
+    unsigned long long* d_keys = (unsigned long long*)d; d += b_keys;
+    unsigned long long* d_sorted = (unsigned long long*)d; d += b_keys;
+    int* d_cnt = (int*)d; d += b_cnt;
+    int* d_pts = (int*)d; d += b_pts;
+    float* d_out = (float*)d; d += b_out;
+    int* d_small = (int*)d;   // [0] max bits, [1] n_keys, [2] n_out
+    VO_CUDA(ctx, cudaMemsetAsync(d_small, 0, b_small, ctx->stream));
+    VO_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, b_cnt, ctx->stream));
+    const double scale = 1.0 / (4.0 * block_size * 255.0);
+    {
+        dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+        gftt_cov_kernel<<<grd, blk, 0, ctx->stream>>>(d_img, g.pitch[0], w, h, (float)scale, (float)(2.0 * scale), d_cov);
+        gftt_box_eig_kernel<<<(w + 127) / 128, 128, 0, ctx->stream>>>(d_cov, w, h, d_eig, d_small);
+        dim3 grd2((w - 2 + 31) / 32, (h - 2 + 7) / 8);
+        gftt_candidates_kernel<<<grd2, blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys, d_small + 1, cap);
+        ctx->launches += 3;
+    }
+    // the candidate count decides the sort; reading it back costs one small sync (the call is synchronous anyway)
+    int* h_small = (int*)(hp + vo_align(npx, 256));
+    VO_CUDA(ctx, cudaMemcpyAsync(h_small, d_small, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int n_keys = h_small[1] < cap ? h_small[1] : cap;
+    if (n_keys == 0) { *n_out = 0; return 0; }
+    const unsigned long long* d_order = d_sorted;
+    if (n_keys <= 32768) {
+        gftt_rank_kernel<<<(n_keys + 255) / 256, 256, 0, ctx->stream>>>(d_keys, d_small + 1, cap, d_sorted);
+        ctx->launches++;
+    } else {
+        int np = 1;
+        while (np < n_keys) np <<= 1;
+        gftt_bitonic_pad_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(d_keys, d_small + 1, cap, np);
+        for (int k = 2; k <= np; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                gftt_bitonic_step_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(d_keys, j, k, np);
+                ctx->launches++;
+            }
+        d_order = d_keys;
+    }
+    gftt_select_kernel<<<1, 32, 0, ctx->stream>>>(d_order, d_small + 1, cap, w, h, max_corners, min_dist, cell, gw, gh, d_cnt,
+                                                  d_pts, d_out, d_small + 2);
+    ctx->launches++;
+    VO_CUDA(ctx, cudaGetLastError());
+    VO_CUDA(ctx, cudaMemcpyAsync(h_small, d_small, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int n = h_small[2];
+    if (n > 0) {
+        VO_TRY(vo_reserve_pinned(ctx, (size_t)n * 8 + 4096));
+        VO_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+        memcpy(corners_xy, ctx->h_pin, (size_t)n * 8);
+    }
+    *n_out = n;
+    return 0;
+}
