@@ -4,9 +4,9 @@
  * Restates cv2.goodFeaturesToTrack(img, maxCorners, quality, minDistance, blockSize=3,
  * useHarrisDetector=False) as called at reference VisualOdometryPipeLine.py:256 (OpenCV
  * modules/imgproc/src/{featureselect,corner}.cpp; third party, not vendored).  Spec: SURVEY.md
- * A.4.  cv2's float32 min-eigenvalue map is not bit-reproducible (its Sobel/box filters sum in
- * SIMD order); what is pinned -- live against cv2 and through tests/golden/gftt.npz -- is the
- * ORDERED corner list, which is what the reference consumes.
+ * A.4.  Pinned live against cv2 and through tests/golden/gftt.npz: the float32 min-eigenvalue map
+ * is BIT-EQUAL to cv2.cornerMinEigenVal and the ordered corner list (what the reference consumes)
+ * is identical, including exact ties between symmetric corners.
  */
 #include "vo_oracle.h"
 #include <math.h>

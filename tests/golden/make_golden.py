@@ -109,7 +109,26 @@ def pnp():
     np.savez_compressed(os.path.join(OUT, "pnp.npz"), **out)
 
 
-ALL = dict(klt_small=klt_small, pnp=pnp)
+def gftt():
+    out = {}
+    s = synth.render_sequence("kitti", 1, seed=11, width=400, height=200)
+    img = s["frames"][0]
+    blobs = np.full((200, 300), 50, np.uint8)
+    for (x, y) in [(20, 20), (100, 30), (200, 50), (50, 100), (150, 120), (250, 150), (30, 170)]:
+        blobs[y:y + 6, x:x + 6] = 200     # seven identical blobs: exact ties, order = descending address
+    out["img"], out["blobs"] = img, blobs
+    out["eig"] = cv2.cornerMinEigenVal(img, 3, ksize=3)
+    cases = [(1400, 0.1, 10.0), (1400, 0.03, 10.0), (2000, 0.001, 3.0), (0, 0.2, 7.5), (500, 0.05, 0.0), (300, 0.01, 1.4), (5, 0.01, 10.0)]
+    out["cases"] = np.array(cases)
+    for name, im in (("img", img), ("blobs", blobs)):
+        for ci, (mc, q, md) in enumerate(cases):
+            c = cv2.goodFeaturesToTrack(im, int(mc), q, md, blockSize=3, useHarrisDetector=False)
+            out[f"{name}_c{ci}"] = c if c is not None else np.zeros((0, 1, 2), np.float32)
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(OUT, "gftt.npz"), **out)
+
+
+ALL = dict(klt_small=klt_small, pnp=pnp, gftt=gftt)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(ALL)
