@@ -1,0 +1,397 @@
+// Brute-force kNN(k=2) + Lowe ratio test for SIFT descriptors (replaces
+// cv2.BFMatcher().knnMatch(d0, d1, k=2) at reference VisualOdometryPipeLine.py:229 and the Python
+// ratio loop at :218-224; spec SURVEY.md A.5).
+//
+// d^2(i,j) = |q_i|^2 + |t_j|^2 - 2 q_i.t_j.  OpenCV's SIFT descriptors are integers 0..255, so fp16
+// operands with fp32 accumulation give the dot products exactly (every partial sum is an integer
+// < 2^24) and the squared distances are exact integers: indices, tie-breaks (lowest train index
+// first) and the ratio decision are bit-exact with cv2.
+//
+// The contraction runs on the 5th-gen tensor cores: tcgen05.mma (cta_group::1, kind::f16,
+// M=128, N=256, K=16 x 8) issued by one thread, operands staged by TMA into 128B-swizzled
+// shared memory, accumulators double-buffered in TMEM (2 x 256 columns).  Four epilogue warps
+// pull the accumulators with tcgen05.ld and keep a running (best, second) per query row in
+// registers -- the Q x T distance matrix is never materialised.  A CTA owns one 128-query tile and
+// a contiguous range of train tiles; partial top-2s of the ranges are merged in index order.
+#include "internal.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#define KNN_BM 128
+#define KNN_BN 256
+#define KNN_DIM 128
+#define KNN_THREADS 192
+#define KNN_A_BYTES (KNN_BM * KNN_DIM * 2)        // 32 KB
+#define KNN_B_BYTES (KNN_BN * KNN_DIM * 2)        // 64 KB per stage
+#define KNN_SMEM (1024 + KNN_A_BYTES + 2 * KNN_B_BYTES + 2 * KNN_BN * 4 + 256)
+#define KNN_BIG 3.0e38f
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    long long spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > (1ll << 26)) __trap();   // a protocol bug must fail loudly, not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------ prep: f32 -> fp16 + norms
+__global__ void __launch_bounds__(256)
+knn_prep_kernel(const float* __restrict__ src, int n, int n_pad, __half* __restrict__ dst, float* __restrict__ norm,
+                float pad_norm, int* __restrict__ bad)
+{
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) v = reinterpret_cast<const float4*>(src + (size_t)row * KNN_DIM)[lane];
+    const float a[4] = {v.x, v.y, v.z, v.w};
+    float s = 0.f;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ok = ok && (a[k] >= 0.f) && (a[k] <= 255.f) && (a[k] == floorf(a[k]));
+        s += a[k] * a[k];
+    }
+    __half2 h0 = __floats2half2_rn(a[0], a[1]), h1 = __floats2half2_rn(a[2], a[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    reinterpret_cast<uint2*>(dst + (size_t)row * KNN_DIM)[lane] = pk;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // exact: integers < 2^24
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) atomicOr(bad, 1);
+    if (lane == 0) norm[row] = row < n ? s : pad_norm;
+}
+
+// ------------------------------------------------------------------ GEMM + fused top-2
+struct KnnPartial { float d1, d2; int i1, i2; };
+
+__global__ void __launch_bounds__(KNN_THREADS, 1)
+knn_gemm_top2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+                     const float* __restrict__ qnorm, const float* __restrict__ tnorm, int n_tiles_total,
+                     int tiles_per_split, KnnPartial* __restrict__ partial, int nq_pad)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base;
+    const uint32_t sB = base + KNN_A_BYTES;
+    const uint32_t sTn = sB + 2 * KNN_B_BYTES;
+    const uint32_t sBar = sTn + 2 * KNN_BN * 4;
+    float* tn_s = reinterpret_cast<float*>(smem_raw + (sTn - smem_u32(smem_raw)));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 128 - smem_u32(smem_raw)));
+    const uint32_t bar_a = sBar, bar_bfull = sBar + 8, bar_bempty = sBar + 24, bar_accfull = sBar + 40, bar_accempty = sBar + 56;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * KNN_BM;
+    const int t0 = blockIdx.y * tiles_per_split;
+    const int t1 = min(t0 + tiles_per_split, n_tiles_total);
+    const int nt = t1 - t0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_bfull + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
+            mbar_init(bar_accfull + 8 * s, 1);
+            mbar_init(bar_accempty + 8 * s, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // query tile: two 64-element K blocks, resident for the whole CTA
+            mbar_expect_tx(bar_a, KNN_A_BYTES);
+            tma_load_2d(sA, &map_q, 0, m0, bar_a);
+            tma_load_2d(sA + KNN_A_BYTES / 2, &map_q, 64, m0, bar_a);
+            for (int i = 0; i < nt; ++i) {
+                const int s = i & 1, ph = (i >> 1) & 1;
+                mbar_wait(bar_bempty + 8 * s, ph ^ 1);
+                mbar_expect_tx(bar_bfull + 8 * s, KNN_B_BYTES);
+                const uint32_t dst = sB + s * KNN_B_BYTES;
+                tma_load_2d(dst, &map_t, 0, (t0 + i) * KNN_BN, bar_bfull + 8 * s);
+                tma_load_2d(dst + KNN_B_BYTES / 2, &map_t, 64, (t0 + i) * KNN_BN, bar_bfull + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=F32, A=B=F16, K-major both, N=256, M=128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(KNN_BN >> 3) << 17) | ((uint32_t)(KNN_BM >> 4) << 24);
+            mbar_wait(bar_a, 0);
+            for (int i = 0; i < nt; ++i) {
+                const int s = i & 1, ph = (i >> 1) & 1;
+                mbar_wait(bar_accempty + 8 * s, ph ^ 1);
+                mbar_wait(bar_bfull + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * KNN_BN);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t adesc = umma_desc_sw128(sA + kb * (KNN_A_BYTES / 2));
+                    const uint64_t bdesc = umma_desc_sw128(sB + s * KNN_B_BYTES + kb * (KNN_B_BYTES / 2));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // 16 fp16 = 32 B per UMMA_K step inside the swizzle atom
+                        tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                }
+                tc_commit(bar_bempty + 8 * s);     // smem stage free once these MMAs have read it
+                tc_commit(bar_accfull + 8 * s);    // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; one query row per thread
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;   // 0..127
+        const float qn = qnorm[row];
+        float b1 = KNN_BIG, b2 = KNN_BIG;
+        int i1 = -1, i2 = -1;
+        for (int i = 0; i < nt; ++i) {
+            const int s = i & 1, ph = (i >> 1) & 1;
+            const int j0 = (t0 + i) * KNN_BN;
+            tn_s[s * KNN_BN + et] = tnorm[j0 + et];
+            tn_s[s * KNN_BN + 128 + et] = tnorm[j0 + 128 + et];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(bar_accfull + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * KNN_BN);
+#pragma unroll 1
+            for (int c = 0; c < KNN_BN / 32; ++c) {
+                uint32_t v[32];
+                tc_ld32(taddr + c * 32, v);
+                tc_ld_wait();
+                const float4* tn4 = reinterpret_cast<const float4*>(tn_s + s * KNN_BN + c * 32);
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const float4 t4 = tn4[e4];
+                    const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // exact integer arithmetic in fp32: (|q|^2 + |t|^2) - 2 q.t
+                        const float d = __fmaf_rn(-2.f, __uint_as_float(v[e4 * 4 + e]), __fadd_rn(qn, tt[e]));
+                        const int j = j0 + c * 32 + e4 * 4 + e;
+                        const bool lt1 = d < b1, lt2 = d < b2;     // strict: the lower train index wins ties
+                        i2 = lt1 ? i1 : (lt2 ? j : i2);
+                        b2 = lt1 ? b1 : (lt2 ? d : b2);
+                        i1 = lt1 ? j : i1;
+                        b1 = lt1 ? d : b1;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_accempty + 8 * s);
+        }
+        KnnPartial p;
+        p.d1 = b1; p.d2 = b2; p.i1 = i1; p.i2 = i2;
+        partial[(size_t)blockIdx.y * nq_pad + row] = p;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// merge the per-range partial top-2s in train-index order, take square roots, apply the ratio test
+__global__ void __launch_bounds__(256)
+knn_finalize_kernel(const KnnPartial* __restrict__ partial, int n_splits, int nq, int nq_pad, int nt, double ratio,
+                    int* __restrict__ idx2, float* __restrict__ dist2, uint8_t* __restrict__ accept)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nq) return;
+    float b1 = KNN_BIG, b2 = KNN_BIG;
+    int i1 = -1, i2 = -1;
+    for (int s = 0; s < n_splits; ++s) {
+        const KnnPartial p = partial[(size_t)s * nq_pad + r];
+        const float ds[2] = {p.d1, p.d2};
+        const int is[2] = {p.i1, p.i2};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float d = ds[k];
+            const int j = is[k];
+            if (j < 0 || j >= nt) continue;
+            const bool lt1 = d < b1, lt2 = d < b2;
+            i2 = lt1 ? i1 : (lt2 ? j : i2);
+            b2 = lt1 ? b1 : (lt2 ? d : b2);
+            i1 = lt1 ? j : i1;
+            b1 = lt1 ? d : b1;
+        }
+    }
+    const float FMAX = 3.402823466e+38f;
+    const float d1 = i1 >= 0 ? __fsqrt_rn(b1) : FMAX;
+    const float d2 = i2 >= 0 ? __fsqrt_rn(b2) : FMAX;
+    idx2[2 * r] = i1; idx2[2 * r + 1] = i2;
+    dist2[2 * r] = d1; dist2[2 * r + 1] = d2;
+    // reference :221  m.distance < feature_ratio * n.distance, evaluated in Python float64
+    accept[r] = (i1 >= 0 && i2 >= 0 && (double)d1 < __dmul_rn(ratio, (double)d2)) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int knn_make_map(b200vo_ctx* ctx, CUtensorMap* map, void* gptr, int rows, int box_rows)
+{
+    if (!ctx->encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
+            return vo_set_err(ctx, 200, "cuTensorMapEncodeTiled entry point unavailable");
+        ctx->encode_tiled = fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)KNN_DIM, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)KNN_DIM * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, gptr, dims, strides, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vo_set_err(ctx, 201, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+// device-resident core: q_dev/t_dev float32 row-major; outputs device pointers
+int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* t_dev, int nt, double ratio,
+                      int* idx2_dev, float* dist2_dev, uint8_t* accept_dev, int* bad_flag_host)
+{
+    const int nq_pad = (int)vo_align((size_t)nq, KNN_BM), nt_pad = (int)vo_align((size_t)nt, KNN_BN);
+    const int m_tiles = nq_pad / KNN_BM, n_tiles = nt_pad / KNN_BN;
+    // split the train range so that the grid covers the SMs; every split keeps tiles in ascending order
+    int n_splits = (ctx->num_sms + m_tiles - 1) / m_tiles;
+    if (n_splits > n_tiles) n_splits = n_tiles;
+    if (n_splits < 1) n_splits = 1;
+    const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
+    n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    const size_t b_q16 = vo_align((size_t)nq_pad * KNN_DIM * 2, 1024), b_t16 = vo_align((size_t)nt_pad * KNN_DIM * 2, 1024);
+    const size_t b_qn = vo_align((size_t)nq_pad * 4, 256), b_tn = vo_align((size_t)nt_pad * 4, 256);
+    const size_t b_part = vo_align((size_t)n_splits * nq_pad * sizeof(KnnPartial), 256);
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[3], b_q16 + b_t16 + b_qn + b_tn + b_part + 256));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[3].p;
+    __half* q16 = (__half*)d; d += b_q16;
+    __half* t16 = (__half*)d; d += b_t16;
+    float* qn = (float*)d; d += b_qn;
+    float* tn = (float*)d; d += b_tn;
+    KnnPartial* part = (KnnPartial*)d; d += b_part;
+    int* bad = (int*)d;
+    VO_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
+    knn_prep_kernel<<<(nq_pad + 7) / 8, 256, 0, ctx->stream>>>(q_dev, nq, nq_pad, q16, qn, 0.f, bad);
+    knn_prep_kernel<<<(nt_pad + 7) / 8, 256, 0, ctx->stream>>>(t_dev, nt, nt_pad, t16, tn, KNN_BIG, bad);
+    ctx->launches += 2;
+    CUtensorMap map_q, map_t;
+    VO_TRY(knn_make_map(ctx, &map_q, q16, nq_pad, KNN_BM));
+    VO_TRY(knn_make_map(ctx, &map_t, t16, nt_pad, KNN_BN));
+    VO_CUDA(ctx, cudaFuncSetAttribute(knn_gemm_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNN_SMEM));
+    knn_gemm_top2_kernel<<<dim3(m_tiles, n_splits), KNN_THREADS, KNN_SMEM, ctx->stream>>>(map_q, map_t, qn, tn, n_tiles,
+                                                                                       tiles_per_split, part, nq_pad);
+    knn_finalize_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(part, n_splits, nq, nq_pad, nt, ratio, idx2_dev, dist2_dev, accept_dev);
+    ctx->launches += 2;
+    VO_CUDA(ctx, cudaGetLastError());
+    if (bad_flag_host) VO_CUDA(ctx, cudaMemcpyAsync(bad_flag_host, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+extern "C" int b200vo_knn2_ratio(b200vo_ctx* ctx, const float* q, int nq, const float* t, int nt, int dim,
+                                 double ratio, int32_t* idx2, float* dist2, uint8_t* accept)
+{
+    if (!ctx || !q || !t || !idx2 || !dist2 || !accept) return B200VO_E_BADARG;
+    if (nq < 0 || nt < 0 || dim <= 0) return vo_set_err(ctx, B200VO_E_BADARG, "type == src2.type() && src1.cols == src2.cols");
+    if (dim != KNN_DIM) return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "descriptor length %d != 128 (SIFT)", dim);
+    if (nq == 0) return 0;
+    if (nt == 0) {
+        for (int i = 0; i < nq; ++i) { idx2[2 * i] = idx2[2 * i + 1] = -1; dist2[2 * i] = dist2[2 * i + 1] = 3.402823466e+38f; accept[i] = 0; }
+        return 0;
+    }
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const size_t b_q = vo_align((size_t)nq * dim * 4, 256), b_t = vo_align((size_t)nt * dim * 4, 256);
+    const size_t b_i = vo_align((size_t)nq * 8, 256), b_d = vo_align((size_t)nq * 8, 256), b_a = vo_align((size_t)nq, 256);
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[4], b_q + b_t + b_i + b_d + b_a));
+    VO_TRY(vo_reserve_pinned(ctx, b_q + b_t + b_i + b_d + b_a + 256));
+    uint8_t* dv = (uint8_t*)ctx->d_scratch[4].p;
+    uint8_t* hp = (uint8_t*)ctx->h_pin;
+    memcpy(hp, q, (size_t)nq * dim * 4);
+    memcpy(hp + b_q, t, (size_t)nt * dim * 4);
+    VO_CUDA(ctx, cudaMemcpyAsync(dv, hp, b_q + b_t, cudaMemcpyHostToDevice, ctx->stream));
+    int* h_bad = (int*)(hp + b_q + b_t + b_i + b_d + b_a);
+    *h_bad = 0;
+    VO_TRY(vo_knn2_ratio_dev(ctx, (const float*)dv, nq, (const float*)(dv + b_q), nt, ratio, (int*)(dv + b_q + b_t),
+                             (float*)(dv + b_q + b_t + b_i), dv + b_q + b_t + b_i + b_d, h_bad));
+    VO_CUDA(ctx, cudaMemcpyAsync(hp + b_q + b_t, dv + b_q + b_t, b_i + b_d + b_a, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    if (*h_bad)
+        return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "descriptors must be integer-valued in 0..255 (cv2 SIFT); other float descriptors are not implemented");
+    memcpy(idx2, hp + b_q + b_t, (size_t)nq * 8);
+    memcpy(dist2, hp + b_q + b_t + b_i, (size_t)nq * 8);
+    memcpy(accept, hp + b_q + b_t + b_i + b_d, (size_t)nq);
+    return 0;
+}

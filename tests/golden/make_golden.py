@@ -128,7 +128,42 @@ def gftt():
     np.savez_compressed(os.path.join(OUT, "gftt.npz"), **out)
 
 
-ALL = dict(klt_small=klt_small, pnp=pnp, gftt=gftt)
+def sift_like(n, seed):
+    """Integer-valued 0..255 descriptors with |d| ~ 512, like cv2 SIFT output."""
+    r = np.random.default_rng(seed)
+    x = r.gamma(0.6, 30, (n, 128))
+    x = x / np.linalg.norm(x, axis=1, keepdims=True) * 512
+    return np.clip(np.rint(x), 0, 255).astype(np.float32)
+
+
+def knn():
+    out = {}
+    rng = np.random.default_rng(0)
+    q, t = sift_like(700, 1), sift_like(900, 2)
+    t[50] = t[100]; q[7] = t[50]          # planted duplicates: tie -> lower train index first
+    t[10] = q[8]; t[800] = q[8]
+    t[300:340] = np.clip(q[100:140] + rng.integers(-6, 7, (40, 128)), 0, 255)   # true matches (ratio accepts)
+    q[20] = 255; t[21] = 255; t[22] = 0    # extreme norms: d^2 = 0 and 128*255^2
+    m = cv2.BFMatcher().knnMatch(q, t, k=2)
+    out["q"], out["t"] = q, t
+    out["idx"] = np.array([[a.trainIdx, b.trainIdx] for a, b in m], np.int32)
+    out["dist"] = np.array([[a.distance, b.distance] for a, b in m], np.float32)
+    out["accept"] = np.array([a.distance < 0.8 * b.distance for a, b in m], np.uint8)
+    # real SIFT descriptors of a synthetic pair (cropped to keep the fixture small)
+    s = synth.render_sequence("kitti", 3, seed=2, width=500, height=250)
+    sift = cv2.SIFT_create()
+    _, d0 = sift.detectAndCompute(s["frames"][0], None)
+    _, d1 = sift.detectAndCompute(s["frames"][2], None)
+    m = cv2.BFMatcher().knnMatch(d0, d1, k=2)
+    out["sq"], out["st"] = d0.astype(np.uint8), d1.astype(np.uint8)
+    out["sidx"] = np.array([[a.trainIdx, b.trainIdx] for a, b in m], np.int32)
+    out["sdist"] = np.array([[a.distance, b.distance] for a, b in m], np.float32)
+    out["saccept"] = np.array([a.distance < 0.8 * b.distance for a, b in m], np.uint8)
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(OUT, "knn.npz"), **out)
+
+
+ALL = dict(klt_small=klt_small, pnp=pnp, gftt=gftt, knn=knn)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(ALL)
