@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""Secondary workloads of BASELINE.json (configs 2-4): per call-site timings through the C-ABI
+(host buffers in, host buffers out) next to the same cv2 call on the host cores.
+
+  python benchmarks/bench_components.py [--only knn,gftt,klt,pnp] [--reps 20]
+
+Prints one JSON object per workload.  `gpu_ms` is CUDA-event time on the ctx stream for the whole
+call (H2D + kernels + D2H), `wall_ms` the median wall clock of the call, `cv2_ms` the median wall
+clock of the cv2 call on all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+def med(f, reps, warm=3):
+    for _ in range(warm):
+        f()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        f()
+        ts.append(time.perf_counter() - t0)
+    return 1e3 * float(np.median(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="knn,gftt,klt,pnp")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--no-cv2", action="store_true")
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    from monocular_visual_odometry_va4mr_b200 import _lib, cv2_compat, synth
+    from make_golden import make_pnp_case, sift_like
+    cv2 = None
+    if not args.no_cv2:
+        try:
+            import cv2
+            cv2.setNumThreads(os.cpu_count() or 1)
+        except ImportError:
+            cv2 = None
+    ctx = _lib.default_context(0)
+
+    if "knn" in only:   # config 3: 8192 x 8192 x 128
+        q, t = sift_like(8192, 1), sift_like(8192, 2)
+        wall = med(lambda: cv2_compat.knn2_ratio(q, t, 0.8), args.reps)
+        gpu = ctx.last_gpu_ms()
+        r = {"workload": "knn2+ratio 8192x8192x128 (config 3)", "wall_ms": wall, "gpu_ms": gpu, "gflop": 2 * 8192 * 8192 * 128 / 1e9}
+        if cv2 is not None:
+            bf = cv2.BFMatcher()
+            r["cv2_ms"] = med(lambda: [m for m, n in bf.knnMatch(q, t, k=2) if m.distance < 0.8 * n.distance], 3, 1)
+        print(json.dumps(r))
+    if "gftt" in only:
+        f = synth.render_sequence("kitti", 1, seed=0)["frames"][0]
+        wall = med(lambda: cv2_compat.goodFeaturesToTrack(f, 1400, 0.1, 10, blockSize=3), args.reps)
+        r = {"workload": "goodFeaturesToTrack 1241x376 (1400, 0.1, 10)", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
+        if cv2 is not None:
+            r["cv2_ms"] = med(lambda: cv2.goodFeaturesToTrack(f, 1400, 0.1, 10, blockSize=3), args.reps)
+        print(json.dumps(r))
+    if "klt" in only:   # config 4 tracker part: 20k points, 21x21, 4 levels
+        s = synth.render_sequence("kitti", 2, seed=0)
+        f0, f1 = s["frames"]
+        pts = synth.grid_corners(f0, 20000, seed=0)
+        kw = dict(winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+        wall = med(lambda: cv2_compat.calcOpticalFlowPyrLK(f0, f1, pts, None, **kw), args.reps)
+        r = {"workload": "calcOpticalFlowPyrLK 1241x376, 20k points, 21x21, maxLevel 3 (config 4)", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
+        if cv2 is not None:
+            r["cv2_ms"] = med(lambda: cv2.calcOpticalFlowPyrLK(f0, f1, pts, None, **kw), 5, 1)
+        print(json.dumps(r))
+        pts2 = pts[:2000]
+        wall = med(lambda: cv2_compat.calcOpticalFlowPyrLK(f0, f1, pts2, None, **kw), args.reps)
+        r = {"workload": "calcOpticalFlowPyrLK 1241x376, 2k points, 21x21, maxLevel 3 (single call, stateless)", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
+        if cv2 is not None:
+            r["cv2_ms"] = med(lambda: cv2.calcOpticalFlowPyrLK(f0, f1, pts2, None, **kw), args.reps)
+        print(json.dumps(r))
+    if "pnp" in only:   # config 4 pose part: 20k correspondences, 2000 hypotheses
+        for n, of, iters in ((20000, 0.3, 2000), (20000, 0.5, 2000), (2000, 0.1, 500)):
+            obj, img, K = make_pnp_case(n, of, 4)
+            kw = dict(flags=2, confidence=0.99, reprojectionError=8.0, iterationsCount=iters)
+            wall = med(lambda: cv2_compat.solvePnPRansac(obj, img, K, np.zeros(4), **kw), args.reps)
+            r = {"workload": f"solvePnPRansac P3P N={n} outliers={of} iters<={iters}", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
+            if cv2 is not None:
+                r["cv2_ms"] = med(lambda: cv2.solvePnPRansac(obj, img, K, np.zeros(4), **kw), 5, 1)
+            print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()

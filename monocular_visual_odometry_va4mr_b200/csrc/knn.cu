@@ -9,8 +9,8 @@
 //
 // The contraction runs on the 5th-gen tensor cores: tcgen05.mma (cta_group::1, kind::f16,
 // M=128, N=256, K=16 x 8) issued by one thread, operands staged by TMA into 128B-swizzled
-// shared memory, accumulators double-buffered in TMEM (2 x 256 columns).  Four epilogue warps
-// pull the accumulators with tcgen05.ld and keep a running (best, second) per query row in
+// shared memory, accumulators double-buffered in TMEM (2 x 256 columns).  Sixteen epilogue warps
+// (four per TMEM lane quadrant) pull the accumulators with tcgen05.ld and keep a running (best, second) per query row in
 // registers -- the Q x T distance matrix is never materialised.  A CTA owns one 128-query tile and
 // a contiguous range of train tiles; partial top-2s of the ranges are merged in index order.
 #include "internal.cuh"
@@ -20,10 +20,11 @@
 #define KNN_BM 128
 #define KNN_BN 256
 #define KNN_DIM 128
-#define KNN_THREADS 192
+#define KNN_EPI_WARPS 16
+#define KNN_THREADS (64 + 32 * KNN_EPI_WARPS)
 #define KNN_A_BYTES (KNN_BM * KNN_DIM * 2)        // 32 KB
 #define KNN_B_BYTES (KNN_BN * KNN_DIM * 2)        // 64 KB per stage
-#define KNN_SMEM (1024 + KNN_A_BYTES + 2 * KNN_B_BYTES + 2 * KNN_BN * 4 + 256)
+#define KNN_SMEM (1024 + KNN_A_BYTES + 2 * KNN_B_BYTES + 2 * KNN_BN * 4 + 256 + KNN_BM * 4 * 4)
 #define KNN_BIG 3.0e38f
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -138,6 +139,7 @@ knn_gemm_top2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t sBar = sTn + 2 * KNN_BN * 4;
     float* tn_s = reinterpret_cast<float*>(smem_raw + (sTn - smem_u32(smem_raw)));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 128 - smem_u32(smem_raw)));
+    float* tau_s = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));   // [128 rows][4 column groups]
     const uint32_t bar_a = sBar, bar_bfull = sBar + 8, bar_bempty = sBar + 24, bar_accfull = sBar + 40, bar_accempty = sBar + 56;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -152,7 +154,7 @@ knn_gemm_top2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             mbar_init(bar_bfull + 8 * s, 1);
             mbar_init(bar_bempty + 8 * s, 1);
             mbar_init(bar_accfull + 8 * s, 1);
-            mbar_init(bar_accempty + 8 * s, 128);
+            mbar_init(bar_accempty + 8 * s, 32 * KNN_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,51 +206,77 @@ knn_gemm_top2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; one query row per thread
+        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; four warps per lane quadrant, each
+        // scanning one 64-column group of every accumulator tile; one query row per thread.
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;   // 0..127
-        const float qn = qnorm[row];
+        const int sub = (warp - 2) >> 2;          // column group 0..3
+        const int rl = q * 32 + lane;             // row inside the tile
+        const int row = m0 + rl;
+        const int et = (warp - 2) * 32 + lane;    // 0..511
+        // ordering uses d' = |t|^2 - 2 q.t (|q|^2 is constant per row and added at the end); exact integers in fp32
         float b1 = KNN_BIG, b2 = KNN_BIG;
         int i1 = -1, i2 = -1;
+        if (et < KNN_BN && nt > 0) tn_s[et] = tnorm[t0 * KNN_BN + et];
+        tau_s[rl * 4 + sub] = KNN_BIG;
         for (int i = 0; i < nt; ++i) {
             const int s = i & 1, ph = (i >> 1) & 1;
             const int j0 = (t0 + i) * KNN_BN;
-            tn_s[s * KNN_BN + et] = tnorm[j0 + et];
-            tn_s[s * KNN_BN + 128 + et] = tnorm[j0 + 128 + et];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float tn_next = 0.f;
+            const bool pre = et < KNN_BN && i + 1 < nt;
+            if (pre) tn_next = tnorm[j0 + KNN_BN + et];        // in flight while this tile is scanned
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            {   // the four warps of a row share their running second-best: anything strictly above the
+                // smallest of them cannot enter the global top-2 (entries lowered this way carry index -1)
+                const float4 t4 = *reinterpret_cast<const float4*>(tau_s + rl * 4);
+                const float tau = fminf(fminf(t4.x, t4.y), fminf(t4.z, t4.w)) + 1.0f;   // integers: next value up
+                if (tau < b2) { b2 = tau; i2 = -1; }
+            }
             mbar_wait(bar_accfull + 8 * s, ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * KNN_BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * KNN_BN + sub * 64);
 #pragma unroll 1
-            for (int c = 0; c < KNN_BN / 32; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
                 tc_ld32(taddr + c * 32, v);
                 tc_ld_wait();
-                const float4* tn4 = reinterpret_cast<const float4*>(tn_s + s * KNN_BN + c * 32);
+                const float4* tn4 = reinterpret_cast<const float4*>(tn_s + s * KNN_BN + sub * 64 + c * 32);
+                const int jc = j0 + sub * 64 + c * 32;
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
                     const float4 t4 = tn4[e4];
-                    const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+                    const float d0 = __fmaf_rn(-2.f, __uint_as_float(v[e4 * 4 + 0]), t4.x);
+                    const float d1 = __fmaf_rn(-2.f, __uint_as_float(v[e4 * 4 + 1]), t4.y);
+                    const float d2 = __fmaf_rn(-2.f, __uint_as_float(v[e4 * 4 + 2]), t4.z);
+                    const float d3 = __fmaf_rn(-2.f, __uint_as_float(v[e4 * 4 + 3]), t4.w);
+                    const float m = fminf(fminf(d0, d1), fminf(d2, d3));
+                    if (m < b2) {   // some lane's running second-best is displaced inside this group of four
+                        const float dd[4] = {d0, d1, d2, d3};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        // exact integer arithmetic in fp32: (|q|^2 + |t|^2) - 2 q.t
-                        const float d = __fmaf_rn(-2.f, __uint_as_float(v[e4 * 4 + e]), __fadd_rn(qn, tt[e]));
-                        const int j = j0 + c * 32 + e4 * 4 + e;
-                        const bool lt1 = d < b1, lt2 = d < b2;     // strict: the lower train index wins ties
-                        i2 = lt1 ? i1 : (lt2 ? j : i2);
-                        b2 = lt1 ? b1 : (lt2 ? d : b2);
-                        i1 = lt1 ? j : i1;
-                        b1 = lt1 ? d : b1;
+                        for (int e = 0; e < 4; ++e) {
+                            const float d = dd[e];
+                            if (d < b2) {   // usually one element of the group, in one or two lanes
+                                const int j = jc + e4 * 4 + e;
+                                const bool lt1 = d < b1;           // strict: ascending j, the lower train index wins ties
+                                i2 = lt1 ? i1 : j;
+                                b2 = lt1 ? b1 : d;
+                                i1 = lt1 ? j : i1;
+                                b1 = lt1 ? d : b1;
+                            }
+                        }
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(bar_accempty + 8 * s);
+            tau_s[rl * 4 + sub] = b2;
+            if (pre) tn_s[(s ^ 1) * KNN_BN + et] = tn_next;
         }
+        const float qn = qnorm[row];
         KnnPartial p;
-        p.d1 = b1; p.d2 = b2; p.i1 = i1; p.i2 = i2;
-        partial[(size_t)blockIdx.y * nq_pad + row] = p;
+        p.d1 = i1 >= 0 ? __fadd_rn(b1, qn) : KNN_BIG;
+        p.d2 = i2 >= 0 ? __fadd_rn(b2, qn) : KNN_BIG;
+        p.i1 = i1; p.i2 = i2;
+        partial[((size_t)blockIdx.y * 4 + sub) * nq_pad + row] = p;
     }
     tc_fence_before();
     __syncthreads();
@@ -267,7 +295,7 @@ knn_finalize_kernel(const KnnPartial* __restrict__ partial, int n_splits, int nq
     if (r >= nq) return;
     float b1 = KNN_BIG, b2 = KNN_BIG;
     int i1 = -1, i2 = -1;
-    for (int s = 0; s < n_splits; ++s) {
+    for (int s = 0; s < 4 * n_splits; ++s) {
         const KnnPartial p = partial[(size_t)s * nq_pad + r];
         const float ds[2] = {p.d1, p.d2};
         const int is[2] = {p.i1, p.i2};
@@ -276,7 +304,8 @@ knn_finalize_kernel(const KnnPartial* __restrict__ partial, int n_splits, int nq
             const float d = ds[k];
             const int j = is[k];
             if (j < 0 || j >= nt) continue;
-            const bool lt1 = d < b1, lt2 = d < b2;
+            // partial lists interleave in train index: order by (distance, index)
+            const bool lt1 = d < b1 || (d == b1 && j < i1), lt2 = d < b2 || (d == b2 && j < i2);
             i2 = lt1 ? i1 : (lt2 ? j : i2);
             b2 = lt1 ? b1 : (lt2 ? d : b2);
             i1 = lt1 ? j : i1;
@@ -325,14 +354,14 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
     const int nq_pad = (int)vo_align((size_t)nq, KNN_BM), nt_pad = (int)vo_align((size_t)nt, KNN_BN);
     const int m_tiles = nq_pad / KNN_BM, n_tiles = nt_pad / KNN_BN;
     // split the train range so that the grid covers the SMs; every split keeps tiles in ascending order
-    int n_splits = (ctx->num_sms + m_tiles - 1) / m_tiles;
+    int n_splits = ctx->num_sms / m_tiles;   // one wave: m_tiles * n_splits <= number of SMs
     if (n_splits > n_tiles) n_splits = n_tiles;
     if (n_splits < 1) n_splits = 1;
     const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
     n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const size_t b_q16 = vo_align((size_t)nq_pad * KNN_DIM * 2, 1024), b_t16 = vo_align((size_t)nt_pad * KNN_DIM * 2, 1024);
     const size_t b_qn = vo_align((size_t)nq_pad * 4, 256), b_tn = vo_align((size_t)nt_pad * 4, 256);
-    const size_t b_part = vo_align((size_t)n_splits * nq_pad * sizeof(KnnPartial), 256);
+    const size_t b_part = vo_align((size_t)4 * n_splits * nq_pad * sizeof(KnnPartial), 256);
     VO_TRY(vo_reserve(ctx, ctx->d_scratch[3], b_q16 + b_t16 + b_qn + b_tn + b_part + 256));
     uint8_t* d = (uint8_t*)ctx->d_scratch[3].p;
     __half* q16 = (__half*)d; d += b_q16;
