@@ -4,7 +4,7 @@
 // All `iters` hypotheses are drawn, solved and scored at once; a sequential replay of the
 // per-hypothesis inlier counts then reproduces OpenCV's "first strictly better model wins,
 // shrink niters" loop, so the winner (and therefore the inlier mask) is the one cv2 returns.
-//   1. pnp_samples_kernel   bit-exact cv::RNG((uint64)-1) 4-subsets (raw stream table + parallel mod)
+//   1. ransac_samples_kernel<4> (ransac.cuh) bit-exact cv::RNG((uint64)-1) 4-subsets (raw stream table + parallel mod)
 //   2. pnp_solve_kernel     one thread per hypothesis: FP64 P3P + 4-point disambiguation
 //   3. pnp_score_kernel     (point tile x hypothesis tile): FP64 projection -> f32 error,
 //                           warp-aggregated inlier counts (ballot+popc, one atomicAdd per warp)
@@ -14,69 +14,9 @@
 #include "internal.cuh"
 #include "mathdev.cuh"
 #include "pnp.cuh"
+#include "ransac.cuh"
 
 using namespace vo;
-
-// ------------------------------------------------------------------------------------------
-// 1. samples
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-pnp_samples_kernel(PnpArgs a)
-{
-    extern __shared__ int s_mod[];   // raw[k] % N
-    const int b = blockIdx.x;
-    const int N = a.n[b];
-    int* out = a.samples + (size_t)b * a.iters * 4;
-    if (N < 4) {
-        for (int k = threadIdx.x; k < a.iters * 4; k += blockDim.x) out[k] = -1;
-        return;
-    }
-    if (N == 4) {   // count == modelPoints: a single direct solve on all four points
-        for (int k = threadIdx.x; k < a.iters * 4; k += blockDim.x) out[k] = k < 4 ? k : -1;
-        return;
-    }
-    for (int k = threadIdx.x; k < a.n_raw; k += blockDim.x) s_mod[k] = (int)(a.rng_raw[k] % (uint32_t)N);
-    __syncthreads();
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    int pos = 0, i0 = 0;
-    while (i0 < a.iters) {
-        const int i = i0 + lane, p = pos + 4 * lane;
-        const bool live = i < a.iters;
-        const bool inb = p + 3 < a.n_raw;
-        int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        bool dup = false;
-        if (live && inb) {
-            s0 = s_mod[p]; s1 = s_mod[p + 1]; s2 = s_mod[p + 2]; s3 = s_mod[p + 3];
-            dup = (s1 == s0) || (s2 == s0) || (s2 == s1) || (s3 == s0) || (s3 == s1) || (s3 == s2);
-        }
-        const unsigned stop = __ballot_sync(0xffffffffu, live && (dup || !inb));
-        const int first = stop ? __ffs(stop) - 1 : 32;
-        if (live && lane < first) {
-            out[4 * i] = s0; out[4 * i + 1] = s1; out[4 * i + 2] = s2; out[4 * i + 3] = s3;
-        }
-        if (first == 32) { i0 += 32; pos += 128; continue; }
-        int npos = 0;
-        if (lane == first) {   // getSubset's redraw loop, sequentially, for this one sample
-            int q = p, idx[4] = {-1, -1, -1, -1};
-            bool okk = true;
-            for (int j = 0; j < 4 && okk; ++j) {
-                for (;;) {
-                    if (q >= a.n_raw) { okk = false; break; }
-                    const int v = s_mod[q++];
-                    bool d = false;
-                    for (int m = 0; m < j; ++m) d = d || (idx[m] == v);
-                    if (!d) { idx[j] = v; break; }
-                }
-            }
-            if (!okk) { idx[0] = idx[1] = idx[2] = idx[3] = -1; a.flags[b] |= 1; q = a.n_raw; }
-            out[4 * i] = idx[0]; out[4 * i + 1] = idx[1]; out[4 * i + 2] = idx[2]; out[4 * i + 3] = idx[3];
-            npos = q;
-        }
-        pos = __shfl_sync(0xffffffffu, npos, first);
-        i0 += first + 1;
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // 2. minimal solver: one thread per hypothesis
@@ -624,8 +564,8 @@ int vo_pnp_launch(b200vo_ctx* ctx, const PnpArgs& a, bool gen_samples)
     if (gen_samples) {
         const size_t smem = (size_t)a.n_raw * sizeof(int);
         if (smem > 48 * 1024)
-            VO_CUDA(ctx, cudaFuncSetAttribute(pnp_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pnp_samples_kernel<<<a.batch, 128, smem, ctx->stream>>>(a);
+            VO_CUDA(ctx, cudaFuncSetAttribute(ransac_samples_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ransac_samples_kernel<4><<<a.batch, 128, smem, ctx->stream>>>(a.rng_raw, a.n_raw, a.n, a.iters, a.samples, a.flags);
         ctx->launches++;
     }
     {

@@ -163,7 +163,51 @@ def knn():
     np.savez_compressed(os.path.join(OUT, "knn.npz"), **out)
 
 
-ALL = dict(klt_small=klt_small, pnp=pnp, gftt=gftt, knn=knn)
+def make_emat_pair(n, out_frac, seed, noise=0.3):
+    """Two views of random landmarks under a KITTI-like forward motion, N(0,noise) px noise and
+    `out_frac` gross outliers in the second view; float32 pixel arrays as the reference passes them."""
+    rng = np.random.default_rng(seed)
+    K = synth.K_KITTI
+    Rg, _ = cv2.Rodrigues(rng.normal(0, 0.03, 3))
+    tg = np.array([0.05, 0.02, -1.6]) + rng.normal(0, 0.05, 3)
+    X = np.column_stack([rng.uniform(-8, 8, n), rng.uniform(-2, 1.6, n), rng.uniform(4, 80, n)])
+    X2 = X @ Rg.T + tg
+    p1 = (X[:, :2] / X[:, 2:3]) * [K[0, 0], K[1, 1]] + [K[0, 2], K[1, 2]]
+    p2 = (X2[:, :2] / X2[:, 2:3]) * [K[0, 0], K[1, 1]] + [K[0, 2], K[1, 2]]
+    p1 = p1 + rng.normal(0, noise, p1.shape)
+    p2 = p2 + rng.normal(0, noise, p2.shape)
+    no = int(out_frac * n)
+    idx = rng.choice(n, no, replace=False)
+    p2[idx] += rng.uniform(-60, 60, (no, 2))
+    return p1.astype(np.float32), p2.astype(np.float32), K.copy()
+
+
+EMAT_CASES = [(1912, 0.1, 0, 0.99, 1.0), (2000, 0.4, 1, 0.99, 1.0), (500, 0.6, 2, 0.99, 1.0), (3000, 0.25, 3, 0.99, 1.0),
+              (200, 0.0, 4, 0.999, 1.0), (50, 0.5, 5, 0.99, 2.0), (8, 0.0, 6, 0.99, 1.0)]
+
+
+def emat():
+    out = dict(cases=np.array(EMAT_CASES))
+    for ci, (n, of, seed, pr, thr) in enumerate(EMAT_CASES):
+        p1, p2, K = make_emat_pair(n, of, seed)
+        E, m = cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=pr, threshold=thr)
+        out[f"c{ci}_p1"], out[f"c{ci}_p2"], out[f"c{ci}_K"], out[f"c{ci}_E"], out[f"c{ci}_mask"] = p1, p2, K, E, m
+    # minimal-solver candidate sets: cv2.findEssentialMat on exactly 5 points returns all models stacked
+    P1, P2, Es, Ns = [], [], [], []
+    for t in range(60):
+        p1, p2, K = make_emat_pair(5, 0.0, 100 + t, 0.0)
+        E, _ = cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.99, threshold=1)
+        k = 0 if E is None else E.shape[0] // 3
+        Epad = np.zeros((30, 3))
+        if k:
+            Epad[:3 * k] = E
+        P1.append(p1); P2.append(p2); Es.append(Epad); Ns.append(k)
+    out.update(min_p1=np.array(P1), min_p2=np.array(P2), min_E=np.array(Es), min_n=np.array(Ns), min_K=K)
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(OUT, "emat.npz"), **out)
+
+
+ALL = dict(klt_small=klt_small, pnp=pnp, gftt=gftt, knn=knn, emat=emat)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(ALL)
