@@ -10,8 +10,10 @@
 //                           det B(z), Aberth roots, back-substitution) -> up to 10 models
 //   emat_score_kernel       (256 points) x (8 samples x <=10 models): Sampson error in double ->
 //                           float32, ballot+popc counts, one atomicAdd per warp
-//   emat_select_kernel      sequential replay of cv2's loop over (sample, model) counts with the
-//                           adaptive iteration bound, then the winner's mask
+//   emat_update_kernel      sequential replay of cv2's loop over (sample, model) counts with the
+//                           adaptive iteration bound; hypotheses go through in chunks of 128 and a
+//                           chunk beyond the bound exits at once (cv2 stops after 10-60 samples)
+//   emat_finish_kernel      the winner's E and mask
 #include "internal.cuh"
 #include "mathdev.cuh"
 #include "ransac.cuh"
@@ -49,19 +51,26 @@ __constant__ signed char EM_TAB[20][20] = {
 
 struct Poly { double c[20]; };
 
-// o = a * b where a has degree <= da (nonzero only on monomials of that degree or lower)
-__device__ inline void pmul(const Poly& a, const Poly& b, Poly& o)
+// Products only ever pair (degree <= 1) x (degree <= 1) and (degree <= 2) x (degree <= 1): iterate
+// over the 4 linear and 10 quadratic-or-lower monomials instead of all 20 x 20 pairs.
+__constant__ signed char EM_LIN[4] = {12, 15, 18, 19};
+__constant__ signed char EM_QUAD[10] = {5, 7, 9, 11, 12, 14, 15, 17, 18, 19};
+template <int NA>
+__device__ inline void pmul_n(const Poly& a, const Poly& b, Poly& o)
 {
     for (int i = 0; i < 20; ++i) o.c[i] = 0;
-    for (int i = 0; i < 20; ++i) {
+    for (int ii = 0; ii < NA; ++ii) {
+        const int i = NA == 4 ? EM_LIN[ii] : EM_QUAD[ii];
         const double ai = a.c[i];
-        if (ai == 0) continue;
-        for (int j = 0; j < 20; ++j) {
-            const int t = EM_TAB[i][j];
-            if (t >= 0) o.c[t] += ai * b.c[j];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = EM_LIN[jj];
+            o.c[EM_TAB[i][j]] += ai * b.c[j];
         }
     }
 }
+#define pmul_ll(a, b, o) pmul_n<4>(a, b, o)    /* linear x linear */
+#define pmul_ql(a, b, o) pmul_n<10>(a, b, o)   /* quadratic x linear */
 __device__ inline void paxpy(Poly& y, const Poly& x, double s)
 {
     for (int i = 0; i < 20; ++i) y.c[i] += s * x.c[i];
@@ -81,12 +90,12 @@ __device__ inline int poly_roots(const double* c, int n, double* re, double* im)
     if (n <= 0) return 0;
     double a[11];
     for (int i = 0; i <= n; ++i) a[i] = c[i] / c[n];
-    double rad = 0;
-    for (int i = 0; i < n; ++i) rad = fmax(rad, fabs(a[i]));
-    rad = 1 + rad;
+    double rad = 0;   // Fujiwara-style root bound: max |a_i|^(1/(n-i))
+    for (int i = 0; i < n; ++i) if (a[i] != 0) rad = fmax(rad, pow(fabs(a[i]), 1.0 / (n - i)));
     if (!isfinite(rad)) return 0;
+    rad = rad > 0 ? 0.7 * rad : 1.0;
     for (int k = 0; k < n; ++k) {
-        const double ang = 6.283185307179586476925286766559 * k / n + 0.4, r = rad * 0.5 * (1 + 0.1 * k / n);
+        const double ang = 6.283185307179586476925286766559 * k / n + 0.4, r = rad * (1 + 0.1 * k / n);
         re[k] = r * cos(ang); im[k] = r * sin(ang);
     }
     for (int it = 0; it < 200; ++it) {
@@ -117,7 +126,7 @@ __device__ inline int poly_roots(const double* c, int n, double* re, double* im)
             const double st = fabs(stepr) + fabs(stepi), sc = fabs(re[k]) + fabs(im[k]) + 1e-300;
             maxstep = fmax(maxstep, st / sc);
         }
-        if (maxstep < 1e-15) break;
+        if (maxstep < 1e-12) break;   // real roots are Newton-polished afterwards
     }
     return n;
 }
@@ -175,8 +184,8 @@ __device__ int five_point(const double* x1, const double* x2, double (*E)[9])
         for (int k = 0; k < 20; ++k) acc.c[k] = 0;
         const int perm[6][4] = {{0, 1, 2, 1}, {1, 2, 0, 1}, {2, 0, 1, 1}, {2, 1, 0, -1}, {1, 0, 2, -1}, {0, 2, 1, -1}};
         for (int p = 0; p < 6; ++p) {
-            pmul(Ep[0][perm[p][0]], Ep[1][perm[p][1]], t1);
-            pmul(t1, Ep[2][perm[p][2]], t2);
+            pmul_ll(Ep[0][perm[p][0]], Ep[1][perm[p][1]], t1);
+            pmul_ql(t1, Ep[2][perm[p][2]], t2);
             paxpy(acc, t2, (double)perm[p][3]);
         }
         for (int k = 0; k < 20; ++k) A[0][k] = acc.c[k];
@@ -186,15 +195,15 @@ __device__ int five_point(const double* x1, const double* x2, double (*E)[9])
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) {
                 for (int k = 0; k < 20; ++k) EEt[i][j].c[k] = 0;
-                for (int k = 0; k < 3; ++k) { pmul(Ep[i][k], Ep[j][k], t1); paxpy(EEt[i][j], t1, 1.0); }
+                for (int k = 0; k < 3; ++k) { pmul_ll(Ep[i][k], Ep[j][k], t1); paxpy(EEt[i][j], t1, 1.0); }
             }
         for (int k = 0; k < 20; ++k) tr.c[k] = EEt[0][0].c[k] + EEt[1][1].c[k] + EEt[2][2].c[k];
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) {
                 Poly acc;
                 for (int k = 0; k < 20; ++k) acc.c[k] = 0;
-                for (int k = 0; k < 3; ++k) { pmul(EEt[i][k], Ep[k][j], t1); paxpy(acc, t1, 2.0); }
-                pmul(tr, Ep[i][j], t1);
+                for (int k = 0; k < 3; ++k) { pmul_ql(EEt[i][k], Ep[k][j], t1); paxpy(acc, t1, 2.0); }
+                pmul_ql(tr, Ep[i][j], t1);
                 paxpy(acc, t1, -1.0);
                 for (int k = 0; k < 20; ++k) A[1 + 3 * i + j][k] = acc.c[k];
             }
@@ -301,6 +310,8 @@ struct EmatArgs {
     int* flags;
     // outputs
     double* E; uint8_t* mask; int* result; // result[0] = found, [1] = iterations run, [2] = winner flat index
+    int* state;                            // [0] current iteration bound (niters), [1] max_good, [2] winner, [3] iterations replayed
+    int chunk_start, chunk_len;
 };
 
 __global__ void __launch_bounds__(256)
@@ -315,8 +326,9 @@ emat_normalize_kernel(EmatArgs a)
 __global__ void __launch_bounds__(32)
 emat_solve_kernel(EmatArgs a)
 {
-    const int it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= a.iters) return;
+    if (a.chunk_start >= a.state[0]) return;   // cv2's adaptive bound was reached in an earlier chunk
+    const int it = a.chunk_start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= a.iters || it >= a.chunk_start + a.chunk_len) return;
     for (int m = 0; m < EM_MAXM; ++m) a.counts[it * EM_MAXM + m] = 0;
     a.nmodels[it] = 0;
     const int* smp = a.samples + 5 * it;
@@ -350,8 +362,10 @@ emat_score_kernel(EmatArgs a)
 {
     __shared__ double s_E[EM_ST * EM_MAXM * 9];
     __shared__ int s_nm[EM_ST];
-    const int it0 = blockIdx.y * EM_ST;
-    const int ns = min(EM_ST, a.iters - it0);
+    if (a.chunk_start >= a.state[0]) return;
+    const int it0 = a.chunk_start + blockIdx.y * EM_ST;
+    const int ns = min(EM_ST, min(a.iters, a.chunk_start + a.chunk_len) - it0);
+    if (ns <= 0) return;
     for (int k = threadIdx.x; k < ns * EM_MAXM * 9; k += blockDim.x) s_E[k] = a.models[(size_t)it0 * EM_MAXM * 9 + k];
     if (threadIdx.x < ns) s_nm[threadIdx.x] = a.nmodels[it0 + threadIdx.x];
     __syncthreads();
@@ -368,34 +382,38 @@ emat_score_kernel(EmatArgs a)
         }
 }
 
-__global__ void __launch_bounds__(256)
-emat_select_kernel(EmatArgs a)
+// replay of cv2's sequential loop over this chunk's (sample, model) counts; shrinks the bound
+__global__ void emat_update_kernel(EmatArgs a)
 {
-    __shared__ int s_win;
-    __shared__ double s_E[9];
-    if (threadIdx.x == 0) {
-        int win = -1, run = 0;
-        const int N = a.n;
-        if (N == 5) { win = a.nmodels[0] > 0 ? 0 : -1; run = 1; }
-        else if (N > 5) {
-            int niters = a.iters > 1 ? a.iters : 1, max_good = 0, it;
-            for (it = 0; it < niters; ++it) {
-                const int nm = a.nmodels[it];
-                for (int m = 0; m < nm; ++m) {
-                    const int good = a.counts[it * EM_MAXM + m];
-                    if (good > (max_good > 4 ? max_good : 4)) {
-                        win = it * EM_MAXM + m; max_good = good;
-                        niters = ransac_update_num_iters(a.conf, (double)(N - good) / N, 5, niters);
-                    }
-                }
-            }
-            run = it;
-        }
-        s_win = win;
-        a.result[0] = win >= 0; a.result[1] = run; a.result[2] = win;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int niters = a.state[0], max_good = a.state[1], win = a.state[2];
+    if (a.chunk_start >= niters) return;
+    const int N = a.n;
+    int it = a.chunk_start;
+    if (N == 5) {
+        if (it == 0) { win = a.nmodels[0] > 0 ? 0 : -1; a.state[2] = win; a.state[3] = 1; a.state[0] = 1; }
+        return;
     }
-    __syncthreads();
-    const int win = s_win;
+    const int end = min(a.chunk_start + a.chunk_len, a.iters);
+    for (; it < end && it < niters; ++it) {
+        const int nm = a.nmodels[it];
+        for (int m = 0; m < nm; ++m) {
+            const int good = a.counts[it * EM_MAXM + m];
+            if (good > (max_good > 4 ? max_good : 4)) {
+                win = it * EM_MAXM + m; max_good = good;
+                niters = ransac_update_num_iters(a.conf, (double)(N - good) / N, 5, niters);
+            }
+        }
+    }
+    a.state[0] = niters; a.state[1] = max_good; a.state[2] = win; a.state[3] = it;
+}
+
+__global__ void __launch_bounds__(256)
+emat_finish_kernel(EmatArgs a)
+{
+    __shared__ double s_E[9];
+    const int win = a.state[2];
+    if (threadIdx.x == 0) { a.result[0] = win >= 0; a.result[1] = a.state[3]; a.result[2] = win; }
     if (win < 0) {
         for (int i = threadIdx.x; i < a.n; i += blockDim.x) a.mask[i] = 0;
         return;
@@ -442,6 +460,7 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
     a.mask = d; d += b_mask;
     uint8_t* d_small = d;                       // E[9] | result[3] | n | flags
     a.E = (double*)d_small; a.result = (int*)(d_small + 128); a.n_dev = (int*)(d_small + 192); a.flags = (int*)(d_small + 256);
+    a.state = (int*)(d_small + 320);
     VO_TRY(vo_reserve_pinned(ctx, 2 * b_p + b_mask + 1024));
     uint8_t* hp = (uint8_t*)ctx->h_pin;
     memcpy(hp, p1, (size_t)n * 8);
@@ -450,7 +469,9 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
     VO_CUDA(ctx, cudaMemsetAsync(d_small, 0, 512, ctx->stream));
     int* h_small = (int*)(hp + 2 * b_p + b_mask);
     h_small[0] = n;
+    h_small[1] = iters; h_small[2] = 0; h_small[3] = -1; h_small[4] = 0;   // state: bound, max_good, winner, replayed
     VO_CUDA(ctx, cudaMemcpyAsync(a.n_dev, h_small, 4, cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA(ctx, cudaMemcpyAsync(a.state, h_small + 1, 16, cudaMemcpyHostToDevice, ctx->stream));
     emat_normalize_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a);
     {
         const size_t smem = (size_t)n_raw * sizeof(int);
@@ -458,10 +479,19 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
             VO_CUDA(ctx, cudaFuncSetAttribute(ransac_samples_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ransac_samples_kernel<5><<<1, 128, smem, ctx->stream>>>(rng, n_raw, a.n_dev, iters, a.samples, a.flags);
     }
-    emat_solve_kernel<<<(iters + 31) / 32, 32, 0, ctx->stream>>>(a);
-    emat_score_kernel<<<dim3((n + 255) / 256, (iters + EM_ST - 1) / EM_ST), 256, 0, ctx->stream>>>(a);
-    emat_select_kernel<<<1, 256, 0, ctx->stream>>>(a);
-    ctx->launches += 5;
+    // chunks of hypotheses in stream order; a chunk whose first sample lies beyond cv2's adaptive
+    // iteration bound (known on the device after the previous chunk) exits immediately
+    const int CH = 128;
+    ctx->launches += 2;
+    for (int c0 = 0; c0 < iters; c0 += CH) {
+        a.chunk_start = c0; a.chunk_len = CH;
+        emat_solve_kernel<<<(CH + 31) / 32, 32, 0, ctx->stream>>>(a);
+        emat_score_kernel<<<dim3((n + 255) / 256, (CH + EM_ST - 1) / EM_ST), 256, 0, ctx->stream>>>(a);
+        emat_update_kernel<<<1, 32, 0, ctx->stream>>>(a);
+        ctx->launches += 3;
+    }
+    emat_finish_kernel<<<1, 256, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
     VO_CUDA(ctx, cudaGetLastError());
     VO_CUDA(ctx, cudaMemcpyAsync(hp, a.mask, b_mask, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(ctx, cudaMemcpyAsync(hp + b_mask, d_small, 512, cudaMemcpyDeviceToHost, ctx->stream));

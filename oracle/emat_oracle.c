@@ -140,7 +140,7 @@ static int poly_roots(const double* c, int n, double* re, double* im)
             double st = fabs(stepr) + fabs(stepi), sc = fabs(re[k]) + fabs(im[k]) + 1e-300;
             if (st / sc > maxstep) maxstep = st / sc;
         }
-        if (maxstep < 1e-15) break;
+        if (maxstep < 1e-12) break;   // real roots are Newton-polished afterwards
     }
     return n;
 }
