@@ -255,6 +255,8 @@ klt_kernel(const KltArgs a)
     }
 }
 
+#include "klt_v2.cuh"
+
 int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,
                    const uint8_t* d_next_slab, size_t next_stride, int batch, const KltPointSet* sets, int n_sets,
                    int n_fixed, const KltParams& kp)
@@ -286,12 +288,12 @@ int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab
     a.smem_iwin = (int)vo_align((size_t)kp.win_w * kp.win_h * 2, 16);
     a.smem_di = (int)vo_align((size_t)kp.win_w * kp.win_h * 4, 16);
     a.smem_per_warp = a.smem_patch + a.smem_der + a.smem_iwin + a.smem_di;
-    const size_t smem = (size_t)a.smem_per_warp * KLT_WARPS;
+    size_t smem = (size_t)a.smem_per_warp * KLT_WARPS;
     const long long total_warps = (long long)batch * (a.cap[0] + a.cap[1]);
     const unsigned grid = (unsigned)((total_warps + KLT_WARPS - 1) / KLT_WARPS);
     void (*kern)(const KltArgs) = nullptr;
-    if (kp.win_w == 21 && kp.win_h == 21) kern = klt_kernel<21, 21>;
-    else if (kp.win_w == 15 && kp.win_h == 15) kern = klt_kernel<15, 15>;
+    if (kp.win_w == 21 && kp.win_h == 21) { kern = klt_kernel_v2<21, 21>; smem = (size_t)KV2<21, 21>::PER_WARP * KLT_WARPS + 64; }
+    else if (kp.win_w == 15 && kp.win_h == 15) { kern = klt_kernel_v2<15, 15>; smem = (size_t)KV2<15, 15>::PER_WARP * KLT_WARPS + 64; }
     else kern = klt_kernel<0, 0>;
     if (smem > 48 * 1024)
         VO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
