@@ -24,11 +24,13 @@ struct KV2 {
     static constexpr int DTASK = DH * DSEG;
     static constexpr int DROUND = (DTASK + 31) / 32;
     static constexpr int DS = ((NSEG * 8 + 1 + 3) / 4) * 4 > DSEG * 8 ? ((NSEG * 8 + 1 + 3) / 4) * 4 : DSEG * 8;  // ints per der row
-    static constexpr int PS = ((WW + 3 + 3 + 3) / 4) * 4 + 8;   // patch row stride (bytes), room for 4-word reads
+    static constexpr int PS0 = ((WW + 3 + 3 + 3) / 4) * 4 + 8;  // patch row stride (bytes), room for 4-word reads
+    static constexpr int PS = (PS0 / 4) % 2 == 0 ? PS0 + 4 : PS0; // odd number of words: rows spread over the banks
     static constexpr int PROWS = WH + 3;
     static constexpr int MARGIN = 4;
     static constexpr int JSV = ((WW + 1 + 2 * MARGIN + 3 + 3) / 4) * 4;   // valid staged bytes per row
-    static constexpr int JS = JSV + 8;                    // row stride (bytes)
+    static constexpr int JS0 = JSV + 8;
+    static constexpr int JS = (JS0 / 4) % 2 == 0 ? JS0 + 4 : JS0;   // row stride (bytes), odd number of words
     static constexpr int JR = WH + 1 + 2 * MARGIN;
     static constexpr int IS = NSEG * 8;                   // Iwin row stride (shorts)
     static constexpr int B_PATCH = ((PS * PROWS + 15) / 16) * 16;

@@ -208,6 +208,71 @@ pnp_select_kernel(PnpArgs a)
 // ------------------------------------------------------------------------------------------
 #define EPNP_T 256
 
+// Symmetric 12x12 eigen-decomposition by two-sided Jacobi rotations, executed by ONE WARP with the
+// round-robin (tournament) ordering: 11 rounds per sweep, 6 disjoint (p,q) pairs per round, all six
+// rotations of a round applied together (columns, then rows, then the eigenvector columns).
+// A (in/out, destroyed) and V (out, eigenvectors in columns) live in shared memory, row-major 12x12.
+// Only used for EPnP's M^T M, where the result is independent of eigenvector signs and of the
+// rotation order (unlike the 3x3 control-point SVD, which replays OpenCV's order exactly).
+__device__ inline void warp_jacobi_eig12(double* A, double* V, double* cs /* [12] */, int lane)
+{
+    for (int k = lane; k < 144; k += 32) V[k] = (k / 12 == k % 12) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        // convergence: sum of squared off-diagonal entries relative to the diagonal
+        double off = 0, dia = 0;
+        for (int k = lane; k < 144; k += 32) {
+            const double v = A[k];
+            if (k / 12 == k % 12) dia += v * v; else off += v * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dia += __shfl_xor_sync(0xffffffffu, dia, o); }
+        if (off <= 1e-30 * dia || off == 0) break;
+        for (int rnd = 0; rnd < 11; ++rnd) {
+            // tournament pairing: player 11 fixed, the others rotate
+            if (lane < 6) {
+                int p = lane == 0 ? 11 : (rnd + lane) % 11;
+                int q = (rnd + 11 - lane) % 11;
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double apq = A[p * 12 + q];
+                double c = 1.0, sn = 0.0;
+                if (fabs(apq) > 1e-300) {
+                    const double theta = (A[q * 12 + q] - A[p * 12 + p]) / (2 * apq);
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                    c = 1 / sqrt(t * t + 1); sn = t * c;
+                }
+                cs[2 * lane] = c; cs[2 * lane + 1] = sn;
+            }
+            __syncwarp();
+            // columns p,q of A and of V: 12 rows x 6 pairs, two matrices
+            for (int e = lane; e < 144; e += 32) {
+                const int m = e / 72, r = (e % 72) / 6, pr = e % 6;
+                int p = pr == 0 ? 11 : (rnd + pr) % 11;
+                int q = (rnd + 11 - pr) % 11;
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double c = cs[2 * pr], sn = cs[2 * pr + 1];
+                double* M = m ? V : A;
+                const double x = M[r * 12 + p], y = M[r * 12 + q];
+                M[r * 12 + p] = c * x - sn * y;
+                M[r * 12 + q] = sn * x + c * y;
+            }
+            __syncwarp();
+            // rows p,q of A
+            for (int e = lane; e < 72; e += 32) {
+                const int k = e / 6, pr = e % 6;
+                int p = pr == 0 ? 11 : (rnd + pr) % 11;
+                int q = (rnd + 11 - pr) % 11;
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double c = cs[2 * pr], sn = cs[2 * pr + 1];
+                const double x = A[p * 12 + k], y = A[q * 12 + k];
+                A[p * 12 + k] = c * x - sn * y;
+                A[q * 12 + k] = sn * x + c * y;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <int NV>
 __device__ __forceinline__ void block_reduce_sum(double* v, double* s_red /* [8][NV] */, double* s_out /* [NV] */)
 {
@@ -397,16 +462,24 @@ pnp_epnp_kernel(PnpArgs a)
     if (threadIdx.x < 4) S.mom_a[threadIdx.x] = S.out[12 + threadIdx.x];
     __syncthreads();
     Xbar[0] = c0[0]; Xbar[1] = c0[1]; Xbar[2] = c0[2];
+    if (threadIdx.x < 32) {
+        double* MtM = S.work;          // destroyed: its diagonal becomes the eigenvalues
+        double* Vm = S.work + 144;     // eigenvectors in columns
+        warp_jacobi_eig12(MtM, Vm, S.work + 288, threadIdx.x);
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            // rows of ut = eigenvectors by DESCENDING eigenvalue (what cvSVD(MtM, D, Ut) returns)
+            int order[12];
+            for (int i = 0; i < 12; ++i) order[i] = i;
+            for (int i = 0; i < 12; ++i)
+                for (int j = i + 1; j < 12; ++j)
+                    if (MtM[order[j] * 13] > MtM[order[i] * 13]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+            for (int i = 0; i < 12; ++i)
+                for (int k = 0; k < 12; ++k) S.ut[12 * i + k] = Vm[12 * k + order[i]];
+        }
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        double* MtM = S.work;
-        double* Um = S.work + 144;
-        double* Vtm = S.work + 288;
-        double W[12];
-        // At workspace: reuse S.ut as scratch, then fill it with the transposed U
-        double* At = S.ut;
-        jacobi_svd<12>(MtM, W, Um, Vtm, At);
-        for (int i = 0; i < 12; ++i)
-            for (int k = 0; k < 12; ++k) S.ut[12 * i + k] = Um[12 * k + i];
         const double* v[4] = {S.ut + 12 * 11, S.ut + 12 * 10, S.ut + 12 * 9, S.ut + 12 * 8};
         const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
         double dv[4][6][3];
