@@ -37,7 +37,7 @@ struct KV2 {
     static constexpr int B_J = ((JS * JR + 15) / 16) * 16;
     static constexpr int B_DER = DS * DH * 4;             // per plane
     static constexpr int B_IWIN = ((IS * WH * 2 + 15) / 16) * 16;
-    static constexpr int PER_WARP = B_PATCH + B_J + 2 * B_DER + B_IWIN;
+    static constexpr int PER_WARP = 2 * B_PATCH + B_J + 2 * B_DER + B_IWIN;   // two patch buffers (prefetch)
 };
 
 __device__ __forceinline__ uint32_t dp2a_lo_u(uint32_t a, uint32_t b, uint32_t c)
@@ -57,6 +57,30 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)   // unsigned p
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+}
+
+// asynchronous global -> shared staging (LDGSTS): the copy proceeds while the warp computes
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n)   // wait until at most n groups are pending
+{
+    if (n <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 2;" ::: "memory");
+}
+template <int WPR, int ROWS>
+__device__ __forceinline__ void stage_rows_async(uint8_t* dst, const uint8_t* src_aligned, int pitch, int lane)
+{
+    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src_aligned);
+    const int pw = pitch >> 2;
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+    for (int k = lane; k < WPR * ROWS; k += 32) {
+        const int r = k / WPR, c = k - r * WPR;
+        cp_async4(d32 + k, srcw + (long long)r * pw + c);
+    }
 }
 
 // 8 interpolated intensities (13-bit, = 32 x grey level) of the run starting at byte offset `off`
@@ -102,11 +126,11 @@ klt_kernel_v2(const KltArgs a)
     if (pi >= n_here) return;
 
     uint8_t* wbase = smem + (size_t)warp * C::PER_WARP;
-    uint8_t* patch = wbase;
-    uint8_t* jreg = wbase + C::B_PATCH;
-    int* derx = reinterpret_cast<int*>(wbase + C::B_PATCH + C::B_J);
+    uint8_t* patch_buf = wbase;                                  // two buffers of B_PATCH
+    uint8_t* jreg = wbase + 2 * C::B_PATCH;
+    int* derx = reinterpret_cast<int*>(wbase + 2 * C::B_PATCH + C::B_J);
     int* dery = derx + C::DS * C::DH;
-    short* Iwin = reinterpret_cast<short*>(wbase + C::B_PATCH + C::B_J + 2 * C::B_DER);
+    short* Iwin = reinterpret_cast<short*>(wbase + 2 * C::B_PATCH + C::B_J + 2 * C::B_DER);
 
     const uint8_t* prev = a.prev + (size_t)seq * a.prev_stride;
     const uint8_t* next = a.next + (size_t)seq * a.next_stride;
@@ -129,6 +153,8 @@ klt_kernel_v2(const KltArgs a)
     float outx = 0.f, outy = 0.f;
     int st = 1;
     float e = 0.f;
+    int pb = 0, pf_level = -1;     // patch buffer in use; level whose patch was prefetched into it
+    const float eps_lo = (float)(a.eps_sq * (1.0 - 1e-6)), eps_hi = (float)(a.eps_sq * (1.0 + 1e-6));
 
     for (int level = a.levels - 1; level >= 0; --level) {
         const int lw = a.w[level], lh = a.h[level], pitch = a.pitch[level];
@@ -149,20 +175,45 @@ klt_kernel_v2(const KltArgs a)
         int iw00, iw01, iw10, iw11;
         bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
 
-        // ---- stage the (WW+3) x (WH+3) neighbourhood of I (origin ip-1), word aligned ----
+        // ---- staging pipeline (cp.async): this level's patch of I was prefetched during the previous
+        // level; now start (1) the window of J around the initial position and (2) the NEXT level's
+        // patch of I (its position depends only on the input point), and overlap both with the
+        // derivative / template arithmetic of this level ----
         __syncwarp();
+        uint8_t* patch = patch_buf + pb * C::B_PATCH;
         const uint8_t* src0 = I + (long long)(ipy - 1) * pitch + (ipx - 1);
         const int mis = (int)(reinterpret_cast<uintptr_t>(src0) & 3);
-        {
-            const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src0 - mis);
-            constexpr int WPR = C::PS / 4;
-            const int pw = pitch >> 2;
-            uint32_t* pw32 = reinterpret_cast<uint32_t*>(patch);
-            for (int k = lane; k < WPR * C::PROWS; k += 32) {
-                const int r = k / WPR, c = k - r * WPR;
-                pw32[k] = __ldg(srcw + (long long)r * pw + c);
-            }
+        if (pf_level != level) {   // not prefetched (top level, or the previous level was skipped)
+            stage_rows_async<C::PS / 4, C::PROWS>(patch, src0 - mis, pitch, lane);
+            cp_async_commit();
         }
+        const float jx0 = __fsub_rn(nx, hwx), jy0 = __fsub_rn(ny, hwy);
+        int rx0 = 0x40000000, ry0 = 0;   // staged J region origin (none)
+        {
+            const int inx = floor_to_int(jx0), iny = floor_to_int(jy0);
+            if (!(inx < -WW || inx >= lw || iny < -WH || iny >= lh)) {
+                ry0 = iny - C::MARGIN;
+                const uint8_t* s0 = J + (long long)ry0 * pitch + (inx - C::MARGIN);
+                const int m2 = (int)(reinterpret_cast<uintptr_t>(s0) & 3);
+                rx0 = inx - C::MARGIN - m2;
+                stage_rows_async<C::JS / 4, C::JR>(jreg, s0 - m2, pitch, lane);
+            }
+            cp_async_commit();
+        }
+        bool pf_next = false;
+        if (level > 0) {
+            const int nl = level - 1;
+            const float sc2 = (float)(1.0 / (double)(1 << nl));
+            const int qx = floor_to_int(__fsub_rn(__fmul_rn(px0, sc2), hwx)), qy = floor_to_int(__fsub_rn(__fmul_rn(py0, sc2), hwy));
+            if (!(qx < -WW || qx >= a.w[nl] || qy < -WH || qy >= a.h[nl])) {
+                const uint8_t* n0 = prev + a.off[nl] + (long long)(qy - 1) * a.pitch[nl] + (qx - 1);
+                const int m3 = (int)(reinterpret_cast<uintptr_t>(n0) & 3);
+                stage_rows_async<C::PS / 4, C::PROWS>(patch_buf + (pb ^ 1) * C::B_PATCH, n0 - m3, a.pitch[nl], lane);
+                pf_next = true;
+            }
+            cp_async_commit();
+        }
+        cp_async_wait_pending(level > 0 ? 2 : 1);   // everything older than (J, next patch): this level's patch
         __syncwarp();
         // patch pixel (x, y), x in [-1, WW+1], y in [-1, WH+1], lives at byte (y+1)*PS + mis + 1 + x
 
@@ -261,15 +312,19 @@ klt_kernel_v2(const KltArgs a)
             __fsub_rn(__fadd_rn(A22, A11),
                       __fsqrt_rn(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12)))),
             (float)(2 * WW * WH));
+        // the prefetched patch becomes the current one at the next level, whatever happens below
+        if (pf_next) { pb ^= 1; pf_level = level - 1; }
         if (minEig < a.min_eig_thr || D < 1.192092896e-07f) {
             if (level == 0) st = 0;
+            cp_async_wait_pending(level > 0 ? 1 : 0);   // drain the J window copy before jreg is reused
             continue;
         }
         D = __fdiv_rn(1.f, D);
-        nx = __fsub_rn(nx, hwx); ny = __fsub_rn(ny, hwy);
+        nx = jx0; ny = jy0;
         float pdx = 0.f, pdy = 0.f;
+        cp_async_wait_pending(level > 0 ? 1 : 0);   // the window of J has landed (the next patch may still fly)
+        __syncwarp();
 
-        int rx0 = 0x40000000, ry0 = 0;   // staged J region origin (none yet)
         for (int j = 0; j < a.max_count; ++j) {
             const int inx = floor_to_int(nx), iny = floor_to_int(ny);
             if (inx < -WW || inx >= lw || iny < -WH || iny >= lh) {
@@ -311,7 +366,12 @@ klt_kernel_v2(const KltArgs a)
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
             outx = __fadd_rn(nx, hwx); outy = __fadd_rn(ny, hwy);
-            if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= a.eps_sq) break;
+            // cv2: delta.ddot(delta) <= eps in double; decided in float unless within 1e-6 of the threshold
+            const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+            bool conv = s2 < eps_lo;
+            if (!conv && !(s2 > eps_hi))
+                conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= a.eps_sq;
+            if (conv) break;
             if (j > 0 && fabsf(__fadd_rn(dx, pdx)) < 0.01f && fabsf(__fadd_rn(dy, pdy)) < 0.01f) {
                 outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f));
                 outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
