@@ -34,6 +34,7 @@ struct KltArgs {
     int win_w, win_h, max_count;
     double eps_sq;
     float min_eig_thr;
+    float eps_lo, eps_hi;   // eps_sq * (1 -+ 1e-6) in float: outside this band the float test decides
     // shared-memory carve-up (bytes, per warp)
     int patch_stride, smem_patch, smem_der, smem_iwin, smem_di, smem_per_warp;
 };
@@ -282,6 +283,7 @@ int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab
     if (a.cap[0] + a.cap[1] <= 0) return 0;
     a.win_w = kp.win_w; a.win_h = kp.win_h; a.max_count = kp.max_count;
     a.eps_sq = kp.eps_sq; a.min_eig_thr = kp.min_eig_thr;
+    a.eps_lo = (float)(kp.eps_sq * (1.0 - 1e-6)); a.eps_hi = (float)(kp.eps_sq * (1.0 + 1e-6));
     a.patch_stride = (int)vo_align((size_t)kp.win_w + 3 + 3, 4);
     a.smem_patch = (int)vo_align((size_t)a.patch_stride * (kp.win_h + 3), 16);
     a.smem_der = (int)vo_align((size_t)(kp.win_w + 1) * (kp.win_h + 1) * 4, 16);

@@ -71,15 +71,22 @@ __device__ __forceinline__ void cp_async_wait_pending(int n)   // wait until at 
     else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 2;" ::: "memory");
 }
+// Each lane owns a fixed (row-in-round, word) slot: 32 / WPR rows per round, so the loop is a
+// pointer increment per copy instead of a division per copy.
 template <int WPR, int ROWS>
 __device__ __forceinline__ void stage_rows_async(uint8_t* dst, const uint8_t* src_aligned, int pitch, int lane)
 {
-    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src_aligned);
-    const int pw = pitch >> 2;
-    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-    for (int k = lane; k < WPR * ROWS; k += 32) {
-        const int r = k / WPR, c = k - r * WPR;
-        cp_async4(d32 + k, srcw + (long long)r * pw + c);
+    constexpr int RPR = 32 / WPR;
+    const int r0 = lane / WPR, c = lane - r0 * WPR;
+    if (r0 >= RPR) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(src_aligned) + (long long)r0 * (pitch >> 2) + c;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst) + r0 * WPR + c;
+    const long long sstep = (long long)RPR * (pitch >> 2);
+#pragma unroll
+    for (int r = 0; r < (ROWS + RPR - 1) / RPR; ++r) {
+        if (r * RPR + r0 < ROWS) cp_async4(d, src);
+        src += sstep;
+        d += RPR * WPR;
     }
 }
 
@@ -154,7 +161,7 @@ klt_kernel_v2(const KltArgs a)
     int st = 1;
     float e = 0.f;
     int pb = 0, pf_level = -1;     // patch buffer in use; level whose patch was prefetched into it
-    const float eps_lo = (float)(a.eps_sq * (1.0 - 1e-6)), eps_hi = (float)(a.eps_sq * (1.0 + 1e-6));
+    const float eps_lo = a.eps_lo, eps_hi = a.eps_hi;
 
     for (int level = a.levels - 1; level >= 0; --level) {
         const int lw = a.w[level], lh = a.h[level], pitch = a.pitch[level];
@@ -339,14 +346,9 @@ klt_kernel_v2(const KltArgs a)
                 const uint8_t* s0 = J + (long long)ry0 * pitch + (inx - C::MARGIN);
                 const int m2 = (int)(reinterpret_cast<uintptr_t>(s0) & 3);
                 rx0 = inx - C::MARGIN - m2;
-                const uint32_t* srcw = reinterpret_cast<const uint32_t*>(s0 - m2);
-                constexpr int WPR = C::JS / 4;
-                const int pw = pitch >> 2;
-                uint32_t* jw = reinterpret_cast<uint32_t*>(jreg);
-                for (int k = lane; k < WPR * C::JR; k += 32) {
-                    const int r = k / WPR, c = k - r * WPR;
-                    jw[k] = __ldg(srcw + (long long)r * pw + c);
-                }
+                stage_rows_async<C::JS / 4, C::JR>(jreg, s0 - m2, pitch, lane);
+                cp_async_commit();
+                cp_async_wait_pending(0);
                 __syncwarp();
             }
             const uint32_t jt = (uint32_t)iw00 | ((uint32_t)iw01 << 16), jb = (uint32_t)iw10 | ((uint32_t)iw11 << 16);
@@ -394,14 +396,9 @@ klt_kernel_v2(const KltArgs a)
                 const uint8_t* s0 = J + (long long)ry0 * pitch + (inx - C::MARGIN);
                 const int m2 = (int)(reinterpret_cast<uintptr_t>(s0) & 3);
                 rx0 = inx - C::MARGIN - m2;
-                const uint32_t* srcw = reinterpret_cast<const uint32_t*>(s0 - m2);
-                constexpr int WPR = C::JS / 4;
-                const int pw = pitch >> 2;
-                uint32_t* jw = reinterpret_cast<uint32_t*>(jreg);
-                for (int k = lane; k < WPR * C::JR; k += 32) {
-                    const int r = k / WPR, c = k - r * WPR;
-                    jw[k] = __ldg(srcw + (long long)r * pw + c);
-                }
+                stage_rows_async<C::JS / 4, C::JR>(jreg, s0 - m2, pitch, lane);
+                cp_async_commit();
+                cp_async_wait_pending(0);
                 __syncwarp();
             }
             const uint32_t jt = (uint32_t)iw00 | ((uint32_t)iw01 << 16), jb = (uint32_t)iw10 | ((uint32_t)iw11 << 16);
