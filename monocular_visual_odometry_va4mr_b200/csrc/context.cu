@@ -1,5 +1,6 @@
 // Context, buffer pool and error plumbing of libb200vo.so.
 #include "internal.cuh"
+#include "tma.cuh"
 #include <cstdarg>
 
 int vo_set_err(b200vo_ctx* ctx, int code, const char* fmt, ...)
@@ -106,5 +107,29 @@ extern "C" int b200vo_sync(b200vo_ctx* ctx)
     if (!ctx) return B200VO_E_BADARG;
     VO_CUDA(ctx, cudaSetDevice(ctx->device));
     VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int vo_encode_tiled(b200vo_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dtype, int rank, void* gptr,
+                    const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                    CUtensorMapSwizzle swizzle)
+{
+    if (!ctx->encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
+            return vo_set_err(ctx, 200, "cuTensorMapEncodeTiled entry point unavailable");
+        ctx->encode_tiled = fn;
+    }
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(map, dtype, (cuuint32_t)rank, gptr, dims, strides_bytes, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vo_set_err(ctx, 201, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }

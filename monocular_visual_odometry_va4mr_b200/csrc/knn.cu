@@ -14,7 +14,7 @@
 // registers -- the Q x T distance matrix is never materialised.  A CTA owns one 128-query tile and
 // a contiguous range of train tiles; partial top-2s of the ranges are merged in index order.
 #include "internal.cuh"
-#include <cuda.h>
+#include "tma.cuh"
 #include <cuda_fp16.h>
 
 #define KNN_BM 128
@@ -27,39 +27,7 @@
 #define KNN_SMEM (1024 + KNN_A_BYTES + 2 * KNN_B_BYTES + 2 * KNN_BN * 4 + 256 + KNN_BM * 4 * 4)
 #define KNN_BIG 3.0e38f
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    long long spins = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && ++spins > (1ll << 26)) __trap();   // a protocol bug must fail loudly, not hang the GPU
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
+// ------------------------------------------------------------------ PTX wrappers (TMA/mbarrier: tma.cuh)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -156,7 +124,7 @@ knn_gemm_top2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             mbar_init(bar_accfull + 8 * s, 1);
             mbar_init(bar_accempty + 8 * s, 32 * KNN_EPI_WARPS);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -322,29 +290,12 @@ knn_finalize_kernel(const KnnPartial* __restrict__ partial, int n_splits, int nq
 }
 
 // ------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static int knn_make_map(b200vo_ctx* ctx, CUtensorMap* map, void* gptr, int rows, int box_rows)
 {
-    if (!ctx->encode_tiled) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
-            return vo_set_err(ctx, 200, "cuTensorMapEncodeTiled entry point unavailable");
-        ctx->encode_tiled = fn;
-    }
     const cuuint64_t dims[2] = {(cuuint64_t)KNN_DIM, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)KNN_DIM * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, gptr, dims, strides, box, estr,
-                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return vo_set_err(ctx, 201, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return 0;
+    return vo_encode_tiled(ctx, map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, gptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // device-resident core: q_dev/t_dev float32 row-major; outputs device pointers
