@@ -44,21 +44,24 @@ class SequenceBatch:
         if rc != 0:
             raise _lib.B200VOError(f"b200vo_batch_create failed ({rc}): {self.ctx.last_error()}")
         self.h = h
-        # host outputs (reused)
+        # host outputs (reused, page-locked so that step() reads them back without a staging copy)
         b, L, Cn = self.batch, self.L, self.Cn
-        self.lm_next = np.zeros((b, L, 2), np.float32)
-        self.lm_status = np.zeros((b, L), np.uint8)
-        self.cand_next = np.zeros((b, max(Cn, 1), 2), np.float32)
-        self.cand_status = np.zeros((b, max(Cn, 1)), np.uint8)
-        self.pose = np.zeros((b, 6), np.float64)
-        self.pnp_ok = np.zeros((b,), np.uint8)
-        self.inlier_mask = np.zeros((b, L), np.uint8)
-        self.n_inliers = np.zeros((b,), np.int32)
+        self.lm_next = self.pinned_empty((b, L, 2), np.float32)
+        self.lm_status = self.pinned_empty((b, L), np.uint8)
+        self.cand_next = self.pinned_empty((b, max(Cn, 1), 2), np.float32)
+        self.cand_status = self.pinned_empty((b, max(Cn, 1)), np.uint8)
+        self.pose = self.pinned_empty((b, 6), np.float64)
+        self.pnp_ok = self.pinned_empty((b,), np.uint8)
+        self.inlier_mask = self.pinned_empty((b, L), np.uint8)
+        self.n_inliers = self.pinned_empty((b,), np.int32)
 
     def close(self):
         if getattr(self, "h", None):
             self.ctx.lib.b200vo_batch_destroy(self.h)
             self.h = None
+            for ptr in getattr(self, "_pinned", []):
+                self.ctx.lib.b200vo_host_free(self.ctx.h, ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -69,6 +72,22 @@ class SequenceBatch:
     def _chk(self, rc, what):
         if rc != 0:
             raise _lib.B200VOError(f"{what} failed ({rc}): {self.ctx.last_error()}")
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array in page-locked host memory (b200vo_host_alloc): DMA'd in place by step()."""
+        dt = np.dtype(dtype)
+        nbytes = max(int(np.prod(shape)) * dt.itemsize, 1)
+        ptr = self.ctx.lib.b200vo_host_alloc(self.ctx.h, nbytes)
+        if not ptr:
+            raise MemoryError("b200vo_host_alloc")
+        self._pinned = getattr(self, "_pinned", []) + [ptr]
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dt, count=int(np.prod(shape))).reshape(shape)
+
+    def pinned_like(self, arr: np.ndarray) -> np.ndarray:
+        out = self.pinned_empty(arr.shape, arr.dtype)
+        out[...] = arr
+        return out
 
     def pinned_frames(self, n_sets: int = 1) -> np.ndarray:
         """(n_sets, batch, rows, cols) uint8 array in page-locked memory (b200vo_host_alloc)."""

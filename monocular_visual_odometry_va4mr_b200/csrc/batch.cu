@@ -7,6 +7,8 @@
 #include "internal.cuh"
 #include "pnp.cuh"
 
+#define B200VO_BATCH_CHUNKS 8
+
 struct b200vo_batch {
     b200vo_ctx* ctx;
     int batch;
@@ -24,6 +26,10 @@ struct b200vo_batch {
     void* pnp_ws;
     const uint32_t* rng; int n_raw;
     bool primed;
+    // host-input path: frames arrive chunk by chunk on a copy stream while earlier chunks are tracked
+    cudaStream_t chunk_stream[B200VO_BATCH_CHUNKS] = {};   // chunk k: H2D -> pyramid -> KLT, all on its own stream
+    cudaEvent_t chunk_ev[B200VO_BATCH_CHUNKS];
+    cudaEvent_t done_ev = nullptr;
     // optional per-kernel timing (CUDA events on the ctx stream): [step][stage] boundaries
     bool profile = false;
     int prof_n = 0;
@@ -124,6 +130,9 @@ extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batc
     B->n_raw = 8 * cfg->pnp_iters + 256;
     if (!rc) rc = vo_rng_table(ctx, B->n_raw, &B->rng);
     if (rc) { b200vo_batch_destroy(B); return rc; }
+    for (auto& st : B->chunk_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (auto& e : B->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&B->done_ev, cudaEventDisableTiming);
     uint8_t* p = (uint8_t*)B->work.p;
     B->c_obj = (float*)p; p += b_obj;
     B->c_img = (float*)p; p += b_img;
@@ -144,6 +153,11 @@ extern "C" void b200vo_batch_destroy(b200vo_batch* B)
     for (auto& s : B->slabs) if (s.p) cudaFree(s.p);
     for (DevBuf* d : {&B->raw, &B->pts_in, &B->outs, &B->work}) if (d->p) cudaFree(d->p);
     if (B->prof_init) for (auto& row : B->prof_ev) for (auto& e : row) cudaEventDestroy(e);
+    if (B->chunk_stream[0]) {
+        for (auto& st : B->chunk_stream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        for (auto& e : B->chunk_ev) cudaEventDestroy(e);
+        cudaEventDestroy(B->done_ev);
+    }
     delete B;
 }
 
@@ -180,25 +194,34 @@ extern "C" int b200vo_batch_prime(b200vo_batch* B, const uint8_t* frames)
 }
 
 // device-resident core: everything after the new frames are in `frames_dev`
-static int batch_core(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts, const float* lm_obj,
-                      const int* n_lm, const float* cand_pts, const int* n_cand, float* lm_next,
-                      uint8_t* lm_status, float* cand_next, uint8_t* cand_status, double* pose, uint8_t* pnp_ok,
-                      uint8_t* inlier_mask, int* n_inliers)
+// pyramids of the new frames + KLT for sequences [b0, b0 + nb)
+static int batch_track(b200vo_batch* B, int b0, int nb, const uint8_t* frames_dev, const float* lm_pts, const int* n_lm,
+                       const float* cand_pts, const int* n_cand, float* lm_next, uint8_t* lm_status, float* cand_next,
+                       uint8_t* cand_status)
 {
     b200vo_ctx* ctx = B->ctx;
     const b200vo_batch_cfg& c = B->cfg;
-    if (!B->primed) return vo_set_err(ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
     const int nxt = B->cur ^ 1;
-    const size_t fb = (size_t)c.rows * c.cols;
-    prof_mark(B, 0);
-    VO_TRY(vo_build_pyramids(ctx, frames_dev, fb, c.rows, c.cols, B->geom, (uint8_t*)B->slabs[nxt].p,
-                             B->geom.slab_bytes, B->batch));
-    prof_mark(B, 1);
-    KltPointSet sets[2] = {{c.max_landmarks, n_lm, lm_pts, lm_next, lm_status, nullptr},
-                           {c.max_candidates, n_cand, cand_pts, cand_next, cand_status, nullptr}};
-    VO_TRY(vo_klt_launch2(ctx, B->geom, (const uint8_t*)B->slabs[B->cur].p, B->geom.slab_bytes,
-                          (const uint8_t*)B->slabs[nxt].p, B->geom.slab_bytes, B->batch, sets,
-                          c.max_candidates > 0 ? 2 : 1, 0, B->kp));
+    const size_t fb = (size_t)c.rows * c.cols, sb = B->geom.slab_bytes;
+    const int L = c.max_landmarks, Cn = c.max_candidates;
+    if (b0 == 0) prof_mark(B, 0);
+    VO_TRY(vo_build_pyramids(ctx, frames_dev + (size_t)b0 * fb, fb, c.rows, c.cols, B->geom,
+                             (uint8_t*)B->slabs[nxt].p + (size_t)b0 * sb, sb, nb));
+    if (b0 == 0 && nb == B->batch) prof_mark(B, 1);
+    KltPointSet sets[2] = {{L, n_lm + b0, lm_pts + (size_t)b0 * L * 2, lm_next + (size_t)b0 * L * 2, lm_status + (size_t)b0 * L, nullptr},
+                           {Cn, n_cand + b0, cand_pts + (size_t)b0 * Cn * 2, cand_next + (size_t)b0 * Cn * 2,
+                            cand_status + (size_t)b0 * Cn, nullptr}};
+    VO_TRY(vo_klt_launch2(ctx, B->geom, (const uint8_t*)B->slabs[B->cur].p + (size_t)b0 * sb, sb,
+                          (const uint8_t*)B->slabs[nxt].p + (size_t)b0 * sb, sb, nb, sets, Cn > 0 ? 2 : 1, 0, B->kp));
+    return 0;
+}
+
+// status==1 compaction, P3P-RANSAC + EPnP, inlier mask -- whole batch
+static int batch_pose(b200vo_batch* B, const float* lm_obj, const int* n_lm, const float* lm_next, const uint8_t* lm_status,
+                      double* pose, uint8_t* pnp_ok, uint8_t* inlier_mask, int* n_inliers)
+{
+    b200vo_ctx* ctx = B->ctx;
+    const b200vo_batch_cfg& c = B->cfg;
     prof_mark(B, 2);
     compact_tracked_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, n_lm, lm_next, lm_status, lm_obj,
                                                               B->c_obj, B->c_img, B->c_n, B->c_orig);
@@ -220,8 +243,19 @@ static int batch_core(b200vo_batch* B, const uint8_t* frames_dev, const float* l
     prof_mark(B, 3);
     if (B->profile && B->prof_n < B200VO_PROF_RING) B->prof_n++;
     VO_CUDA(ctx, cudaGetLastError());
-    B->cur = nxt;
+    B->cur ^= 1;
     return 0;
+}
+
+// device-resident core: everything after the new frames are in `frames_dev`
+static int batch_core(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts, const float* lm_obj,
+                      const int* n_lm, const float* cand_pts, const int* n_cand, float* lm_next,
+                      uint8_t* lm_status, float* cand_next, uint8_t* cand_status, double* pose, uint8_t* pnp_ok,
+                      uint8_t* inlier_mask, int* n_inliers)
+{
+    if (!B->primed) return vo_set_err(B->ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
+    VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status));
+    return batch_pose(B, lm_obj, n_lm, lm_next, lm_status, pose, pnp_ok, inlier_mask, n_inliers);
 }
 
 extern "C" int b200vo_batch_step_dev(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts_dev,
@@ -267,40 +301,78 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     cudaGetLastError();
     VO_TRY(vo_reserve_pinned(ctx, (pinned ? 0 : f_total) + in_bytes + out_bytes));
     uint8_t* hp = (uint8_t*)ctx->h_pin;
+    if (!B->primed) return vo_set_err(ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
     const uint8_t* fsrc = frames;
     if (!pinned) { memcpy(hp, frames, f_total); fsrc = hp; hp += f_total; }
-    VO_CUDA(ctx, cudaMemcpyAsync(B->raw.p, fsrc, f_total, cudaMemcpyHostToDevice, ctx->stream));
-    memcpy(hp + o_lmp, lm_pts, (size_t)nb * L * 8);
-    memcpy(hp + o_lmo, lm_obj, (size_t)nb * L * 12);
-    memcpy(hp + o_nlm, n_lm, (size_t)nb * 4);
-    if (Cn > 0 && cand_pts && n_cand) {
-        memcpy(hp + o_cp, cand_pts, (size_t)nb * Cn * 8);
-        memcpy(hp + o_nc, n_cand, (size_t)nb * 4);
-    } else {
-        memset(hp + o_nc, 0, (size_t)nb * 4);
-    }
+    // Sequences are processed in chunks, each on its own stream: H2D of its frames -> pyramids -> KLT.
+    // The copies queue on the DMA engine in order, so chunk k+1 is on the wire while chunk k is tracked,
+    // and the long-iteration tail of one chunk's KLT overlaps the next chunk's body.
+    const int nchunks = nb >= 2 * B200VO_BATCH_CHUNKS ? B200VO_BATCH_CHUNKS : 1;
+    const int per = (nb + nchunks - 1) / nchunks;
+    // small inputs: page-locked caller arrays are DMA'd in place, pageable ones go through the staging block
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a{};
+        const bool r = p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return r;
+    };
     uint8_t* di = (uint8_t*)B->pts_in.p;
-    VO_CUDA(ctx, cudaMemcpyAsync(di, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    auto upload = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+        if (!src || bytes == 0) return cudaSuccess;
+        if (is_pinned(src)) return cudaMemcpyAsync(di + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        memcpy(hp + off, src, bytes);
+        return cudaMemcpyAsync(di + off, hp + off, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    VO_CUDA(ctx, upload(o_lmp, lm_pts, (size_t)nb * L * 8));
+    VO_CUDA(ctx, upload(o_lmo, lm_obj, (size_t)nb * L * 12));
+    VO_CUDA(ctx, upload(o_nlm, n_lm, (size_t)nb * 4));
+    if (Cn > 0 && cand_pts && n_cand) {
+        VO_CUDA(ctx, upload(o_cp, cand_pts, (size_t)nb * Cn * 8));
+        VO_CUDA(ctx, upload(o_nc, n_cand, (size_t)nb * 4));
+    } else {
+        VO_CUDA(ctx, cudaMemsetAsync(di + o_nc, 0, (size_t)nb * 4, ctx->stream));
+    }
+    VO_CUDA(ctx, cudaEventRecord(B->done_ev, ctx->stream));   // points uploaded; previous step fully retired
     uint8_t* dq = (uint8_t*)B->outs.p;
-    VO_TRY(batch_core(B, (const uint8_t*)B->raw.p, (const float*)(di + o_lmp), (const float*)(di + o_lmo),
-                      (const int*)(di + o_nlm), (const float*)(di + o_cp), (const int*)(di + o_nc),
-                      (float*)(dq + q_lmn), dq + q_lms, (float*)(dq + q_cn), dq + q_cs, (double*)(dq + q_pose),
-                      dq + q_ok, dq + q_mask, (int*)(dq + q_ni)));
+    cudaStream_t main_stream = ctx->stream;
+    int rc_chunks = 0;
+    for (int k = 0; k < nchunks && !rc_chunks; ++k) {
+        const int b0 = k * per, n_here = (b0 + per <= nb ? per : nb - b0);
+        if (n_here <= 0) break;
+        cudaStream_t cs = nchunks > 1 ? B->chunk_stream[k] : main_stream;
+        if (nchunks > 1) VO_CUDA(ctx, cudaStreamWaitEvent(cs, B->done_ev, 0));
+        VO_CUDA(ctx, cudaMemcpyAsync((uint8_t*)B->raw.p + (size_t)b0 * fb, fsrc + (size_t)b0 * fb, (size_t)n_here * fb,
+                                     cudaMemcpyHostToDevice, cs));
+        ctx->stream = cs;   // the launch helpers enqueue on ctx->stream
+        rc_chunks = batch_track(B, b0, n_here, (const uint8_t*)B->raw.p, (const float*)(di + o_lmp), (const int*)(di + o_nlm),
+                                (const float*)(di + o_cp), (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms,
+                                (float*)(dq + q_cn), dq + q_cs);
+        ctx->stream = main_stream;
+        if (!rc_chunks && nchunks > 1) {
+            VO_CUDA(ctx, cudaEventRecord(B->chunk_ev[k], cs));
+            VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->chunk_ev[k], 0));
+        }
+    }
+    if (rc_chunks) return rc_chunks;
+    VO_TRY(batch_pose(B, (const float*)(di + o_lmo), (const int*)(di + o_nlm), (const float*)(dq + q_lmn), dq + q_lms,
+                      (double*)(dq + q_pose), dq + q_ok, dq + q_mask, (int*)(dq + q_ni)));
     uint8_t* ho = hp + in_bytes;
-    VO_CUDA(ctx, cudaMemcpyAsync(ho, dq, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    struct OutCopy { void* dst; size_t off, bytes; bool staged; };
+    OutCopy outs[8] = {{lm_next, q_lmn, (size_t)nb * L * 8, false}, {lm_status, q_lms, (size_t)nb * L, false},
+                       {Cn > 0 ? cand_next : nullptr, q_cn, (size_t)nb * Cn * 8, false},
+                       {Cn > 0 ? cand_status : nullptr, q_cs, (size_t)nb * Cn, false},
+                       {pose, q_pose, (size_t)nb * 48, false}, {pnp_ok, q_ok, (size_t)nb, false},
+                       {inlier_mask, q_mask, (size_t)nb * L, false}, {n_inliers, q_ni, (size_t)nb * 4, false}};
+    for (auto& o : outs) {
+        if (!o.dst || o.bytes == 0) continue;
+        o.staged = !is_pinned(o.dst);
+        VO_CUDA(ctx, cudaMemcpyAsync(o.staged ? (void*)(ho + o.off) : o.dst, dq + o.off, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
-    memcpy(lm_next, ho + q_lmn, (size_t)nb * L * 8);
-    memcpy(lm_status, ho + q_lms, (size_t)nb * L);
-    if (Cn > 0 && cand_next && cand_status) {
-        memcpy(cand_next, ho + q_cn, (size_t)nb * Cn * 8);
-        memcpy(cand_status, ho + q_cs, (size_t)nb * Cn);
-    }
-    memcpy(pose, ho + q_pose, (size_t)nb * 48);
-    memcpy(pnp_ok, ho + q_ok, (size_t)nb);
-    memcpy(inlier_mask, ho + q_mask, (size_t)nb * L);
-    memcpy(n_inliers, ho + q_ni, (size_t)nb * 4);
+    for (auto& o : outs)
+        if (o.dst && o.bytes && o.staged) memcpy(o.dst, ho + o.off, o.bytes);
     return 0;
 }
 
