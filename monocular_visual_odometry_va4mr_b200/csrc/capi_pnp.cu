@@ -20,6 +20,7 @@ static int pnp_run(b200vo_ctx* ctx, const float* obj, const float* img, int n, c
     a.fx = K[0]; a.fy = K[4]; a.cx = K[2]; a.cy = K[5];
     a.thr_sq = (float)((double)reproj_err * (double)reproj_err);
     a.conf = conf;
+    a.full_counts = counts_out != nullptr;
     a.n_raw = 8 * iters + 256;
     VO_TRY(vo_rng_table(ctx, a.n_raw, &a.rng_raw));
     // device layout: [obj | img | n | inliers | mask | pose | ok] + workspace

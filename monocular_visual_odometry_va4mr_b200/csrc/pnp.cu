@@ -25,8 +25,9 @@ __global__ void __launch_bounds__(64)
 pnp_solve_kernel(PnpArgs a)
 {
     const int b = blockIdx.y;
-    const int it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= a.iters) return;
+    const int it = a.h_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= a.h_end) return;
+    if (!a.head && it >= a.need[b]) return;      // the sequential loop can no longer reach this hypothesis
     const size_t hidx = (size_t)b * a.iters + it;
     a.counts[hidx] = 0;
     a.hyp_ok[hidx] = 0;
@@ -77,6 +78,7 @@ pnp_solve_kernel(PnpArgs a)
 // 3. scoring
 // ------------------------------------------------------------------------------------------
 #define SCORE_HT 32   // hypotheses per block
+#define PNP_HEAD 32   // hypotheses solved and scored before the first look at the adaptive stop
 
 __device__ __forceinline__ bool pnp_is_inlier(const double* h, double fx, double fy, double cx, double cy,
                                               double X, double Y, double Z, float iu, float iv, float thr_sq)
@@ -89,6 +91,38 @@ __device__ __forceinline__ bool pnp_is_inlier(const double* h, double fx, double
     return e <= thr_sq;                              // NaN compares false
 }
 
+// Head chunk bookkeeping: the LAST CTA of a sequence to finish (ticket counter, no waiting) replays
+// cv2's loop over the head hypotheses; what it leaves in `niters` bounds every later replay, so
+// the tail launches skip hypotheses >= need[b] (typically all of them: at 10 % outliers cv2 itself
+// stops after ~5 iterations).
+__device__ __forceinline__ void pnp_head_done(const PnpArgs& a, int b, int N)
+{
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(a.ticket + b, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    int niters = a.iters > 1 ? a.iters : 1;
+    if (N == 4) niters = 1;
+    else if (N > 4) {
+        const size_t hb = (size_t)b * a.iters;
+        int max_good = 0;
+        for (int it = a.h_begin; it < a.h_end && it < niters; ++it) {
+            if (!((volatile int*)a.hyp_ok)[hb + it]) continue;
+            const int good = ((volatile int*)a.counts)[hb + it];
+            if (good > (max_good > 3 ? max_good : 3)) {
+                max_good = good;
+                niters = ransac_update_num_iters(a.conf, (double)(N - good) / N, 4, niters);
+            }
+        }
+    } else niters = 0;
+    a.need[b] = niters;
+}
+
 __global__ void __launch_bounds__(256)
 pnp_score_kernel(PnpArgs a)
 {
@@ -97,9 +131,10 @@ pnp_score_kernel(PnpArgs a)
     const int b = blockIdx.z;
     const int N = a.n[b];
     const int p0 = blockIdx.x * blockDim.x;
-    if (p0 >= N || N <= 4) return;
-    const int h0 = blockIdx.y * SCORE_HT;
-    const int nh = min(SCORE_HT, a.iters - h0);
+    const int h0 = a.h_begin + blockIdx.y * SCORE_HT;
+    if (!a.head && (p0 >= N || N <= 4 || h0 >= a.need[b])) return;
+    if (a.head && (p0 >= N || N <= 4)) { pnp_head_done(a, b, N); return; }
+    const int nh = min(SCORE_HT, a.h_end - h0);
     const size_t hbase = (size_t)b * a.iters + h0;
     for (int k = threadIdx.x; k < nh * 12; k += blockDim.x) s_h[k] = a.hyp[hbase * 12 + k];
     if (threadIdx.x < nh) s_ok[threadIdx.x] = a.hyp_ok[hbase + threadIdx.x];
@@ -121,6 +156,7 @@ pnp_score_kernel(PnpArgs a)
         const unsigned m = __ballot_sync(0xffffffffu, in);
         if (lane == 0 && m) atomicAdd(a.counts + hbase + h, __popc(m));
     }
+    if (a.head) pnp_head_done(a, b, N);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -610,7 +646,8 @@ size_t vo_pnp_workspace_bytes(int batch, int cap, int iters)
     b += vo_align((size_t)batch * iters * 12 * sizeof(double), 256);   // hyp
     b += vo_align((size_t)batch * iters * 3 * sizeof(double), 256);    // hyp_rvec
     b += 2 * vo_align((size_t)batch * iters * sizeof(int), 256);       // hyp_ok, counts
-    b += 5 * vo_align((size_t)batch * sizeof(int), 256);               // winner, iters_run, n_inliers, flags, ok_ws
+    b += 4 * vo_align((size_t)batch * sizeof(int), 256);               // winner, iters_run, n_inliers, ok_ws
+    b += vo_align((size_t)batch * 3 * sizeof(int), 256);               // flags | ticket | need
     return b;
 }
 
@@ -626,14 +663,16 @@ void vo_pnp_carve_workspace(PnpArgs& a, void* ws)
     a.winner = (int*)take((size_t)a.batch * sizeof(int));
     a.iters_run = (int*)take((size_t)a.batch * sizeof(int));
     a.n_inliers = (int*)take((size_t)a.batch * sizeof(int));
-    a.flags = (int*)take((size_t)a.batch * sizeof(int));
+    a.flags = (int*)take((size_t)a.batch * 3 * sizeof(int));
+    a.ticket = a.flags + a.batch;
+    a.need = a.flags + 2 * a.batch;
     a.ok_ws = (uint8_t*)take((size_t)a.batch * sizeof(int));
 }
 
 int vo_pnp_launch(b200vo_ctx* ctx, const PnpArgs& a, bool gen_samples)
 {
     if (a.batch <= 0) return 0;
-    VO_CUDA(ctx, cudaMemsetAsync(a.flags, 0, (size_t)a.batch * sizeof(int), ctx->stream));
+    VO_CUDA(ctx, cudaMemsetAsync(a.flags, 0, (size_t)a.batch * 3 * sizeof(int), ctx->stream));
     if (gen_samples) {
         const size_t smem = (size_t)a.n_raw * sizeof(int);
         if (smem > 48 * 1024)
@@ -641,15 +680,21 @@ int vo_pnp_launch(b200vo_ctx* ctx, const PnpArgs& a, bool gen_samples)
         ransac_samples_kernel<4><<<a.batch, 128, smem, ctx->stream>>>(a.rng_raw, a.n_raw, a.n, a.iters, a.samples, a.flags);
         ctx->launches++;
     }
-    {
-        dim3 grid((a.iters + 63) / 64, a.batch);
-        pnp_solve_kernel<<<grid, 64, 0, ctx->stream>>>(a);
-        ctx->launches++;
-    }
-    {
-        dim3 grid((a.cap + 255) / 256, (a.iters + SCORE_HT - 1) / SCORE_HT, a.batch);
-        pnp_score_kernel<<<grid, 256, 0, ctx->stream>>>(a);
-        ctx->launches++;
+    // head chunk: the first PNP_HEAD hypotheses; its last scoring CTA per sequence leaves need[b].
+    // tail chunk: whatever the replay can still reach (CTAs beyond need[b] exit at once).
+    const int head_n = (a.full_counts || a.iters < PNP_HEAD) ? a.iters : PNP_HEAD;
+    for (int part = 0; part < 2; ++part) {
+        PnpArgs c = a;
+        c.head = part == 0;
+        c.h_begin = part == 0 ? 0 : head_n;
+        c.h_end = part == 0 ? head_n : a.iters;
+        const int nh = c.h_end - c.h_begin;
+        if (nh <= 0) continue;
+        dim3 g1((nh + 63) / 64, a.batch);
+        pnp_solve_kernel<<<g1, 64, 0, ctx->stream>>>(c);
+        dim3 g2((a.cap + 255) / 256, (nh + SCORE_HT - 1) / SCORE_HT, a.batch);
+        pnp_score_kernel<<<g2, 256, 0, ctx->stream>>>(c);
+        ctx->launches += 2;
     }
     pnp_select_kernel<<<a.batch, 256, 0, ctx->stream>>>(a);
     ctx->launches++;

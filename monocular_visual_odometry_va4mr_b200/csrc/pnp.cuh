@@ -25,6 +25,11 @@ struct PnpArgs {
     int* iters_run;         // [batch]
     int* n_inliers;         // [batch]
     int* flags;             // [batch] bit0: raw RNG table exhausted
+    int* ticket;            // [batch] CTAs of the head scoring pass that have finished
+    int* need;              // [batch] hypotheses the replay can still reach after the head chunk
+    int h_begin, h_end;     // hypothesis range of this solve/score launch
+    int full_counts;        // 1: score every hypothesis (the caller reads counts[]); no early exit
+    int head;               // 1: this is the head chunk (computes need[]); 0: tail chunk (honours need[])
     uint8_t* ok_ws;         // [batch] spare per-sequence success flags (callers may point `ok` here)
     // outputs
     int* inliers;           // [batch][cap] ascending indices
