@@ -146,12 +146,21 @@ int b200vo_batch_prime(b200vo_batch* b, const uint8_t* frames);
  * pose double (batch,6) = rvec|tvec; pnp_ok uint8 (batch); inlier_mask uint8 (batch,max_landmarks)
  * over the landmark slots (0 for untracked); n_inliers int32 (batch).
  * The new frame becomes the sequence's previous frame for the next step.
+ * frames == NULL consumes the oldest frame set handed over by b200vo_batch_submit_frames.
+ * Page-locked arrays (b200vo_host_alloc) are DMA'd in place; pageable ones are staged.
  */
 int b200vo_batch_step(b200vo_batch* b, const uint8_t* frames, const float* lm_pts,
                       const float* lm_obj, const int32_t* n_lm, const float* cand_pts,
                       const int32_t* n_cand, float* lm_next, uint8_t* lm_status, float* cand_next,
                       uint8_t* cand_status, double* pose, uint8_t* pnp_ok, uint8_t* inlier_mask,
                       int32_t* n_inliers);
+/*
+ * Frames of a FUTURE step (a video reader knows them before the tracker needs them): the copy to
+ * the device and the pyramid build run on a side stream and overlap the kernels of the step in
+ * flight.  frames must be page-locked (b200vo_host_alloc) and stay untouched until the step that
+ * consumes them (b200vo_batch_step with frames == NULL) has returned.  At most two sets may wait.
+ */
+int b200vo_batch_submit_frames(b200vo_batch* b, const uint8_t* frames);
 /* Same step with every input already resident in device memory and outputs left there
  * (bench.py `value`: no host<->device copies in the timed region).  Asynchronous on the
  * ctx stream; pair with b200vo_sync. */

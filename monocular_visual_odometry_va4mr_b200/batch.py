@@ -104,10 +104,17 @@ class SequenceBatch:
         frames = np.ascontiguousarray(frames, np.uint8).reshape(self.batch, self.rows, self.cols)
         self._chk(self.ctx.lib.b200vo_batch_prime(self.h, _p(frames, c_u8p)), "b200vo_batch_prime")
 
+    def submit_frames(self, frames: np.ndarray):
+        """Hand over the frames of a FUTURE step (page-locked array from pinned_frames()): their upload and
+        pyramid build overlap the step in flight; the step called with frames=None consumes them."""
+        assert frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.size == self.batch * self.rows * self.cols
+        self._chk(self.ctx.lib.b200vo_batch_submit_frames(self.h, _p(frames, c_u8p)), "b200vo_batch_submit_frames")
+
     def step(self, frames, lm_pts, lm_obj, n_lm, cand_pts=None, n_cand=None):
-        """Host buffers in, host buffers out (synchronous).  Returns a dict of views on reused arrays."""
+        """Host buffers in, host buffers out (synchronous).  Returns a dict of views on reused arrays.
+        frames=None: use the oldest frame set given to submit_frames()."""
         b, L, Cn = self.batch, self.L, self.Cn
-        assert frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.size == b * self.rows * self.cols
+        assert frames is None or (frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.size == b * self.rows * self.cols)
         assert lm_pts.dtype == np.float32 and lm_pts.shape == (b, L, 2) and lm_pts.flags.c_contiguous
         assert lm_obj.dtype == np.float32 and lm_obj.shape == (b, L, 3) and lm_obj.flags.c_contiguous
         assert n_lm.dtype == np.int32 and n_lm.shape == (b,)
@@ -115,7 +122,7 @@ class SequenceBatch:
             assert cand_pts is not None and cand_pts.dtype == np.float32 and cand_pts.shape == (b, Cn, 2)
             assert n_cand is not None and n_cand.dtype == np.int32 and n_cand.shape == (b,)
         rc = self.ctx.lib.b200vo_batch_step(
-            self.h, _p(frames, c_u8p), _p(lm_pts, c_f32p), _p(lm_obj, c_f32p), _p(n_lm, c_i32p),
+            self.h, _p(frames, c_u8p) if frames is not None else None, _p(lm_pts, c_f32p), _p(lm_obj, c_f32p), _p(n_lm, c_i32p),
             _p(cand_pts, c_f32p) if Cn > 0 else None, _p(n_cand, c_i32p) if Cn > 0 else None,
             _p(self.lm_next, c_f32p), _p(self.lm_status, c_u8p), _p(self.cand_next, c_f32p),
             _p(self.cand_status, c_u8p), _p(self.pose, c_f64p), _p(self.pnp_ok, c_u8p),

@@ -104,3 +104,34 @@ def test_batch_live_cv2(wl):
                                                      flags=cv2.SOLVEPNP_P3P, confidence=opts["pnp_conf"],
                                                      reprojectionError=opts["pnp_err"], iterationsCount=opts["pnp_iters"])
                 assert np.array_equal(np.flatnonzero(o["inlier_mask"][s]), np.flatnonzero(keep)[inl.ravel()])
+
+
+def test_prefetched_frames_equal_call_by_call(wl):
+    """b200vo_batch_submit_frames(t+1) + step(frames=None) must give the bits of step(frames)."""
+    opts = workload.REFERENCE_OPTIONS["kitti"]
+    n_steps = 5
+    order, ref = _run_steps(wl, n_steps, opts, pinned=True)
+    sb = SequenceBatch(wl.batch, wl.h, wl.w, wl.K, win=opts["win"], max_level=opts["max_level"], criteria=opts["criteria"],
+                       pnp_iters=opts["pnp_iters"], pnp_reproj_err=opts["pnp_err"], pnp_conf=opts["pnp_conf"],
+                       max_landmarks=wl.L, max_candidates=wl.Cn)
+    frames = sb.pinned_frames(wl.F)
+    frames[:] = wl.frames
+    sb.prime(frames[order[0]])
+    sb.submit_frames(frames[order[1]])
+    for t in range(n_steps):
+        f = order[t]
+        if t + 2 <= n_steps:
+            sb.submit_frames(frames[order[t + 2]])     # two sets waiting at most
+        o = sb.step(None, wl.lm_pts[f], wl.lm_obj[f], wl.n_lm[f], wl.cand_pts[f], wl.n_cand[f])
+        for k, v in o.items():
+            assert np.array_equal(v, ref[t][k]), (t, k)
+    # protocol errors: nothing submitted / a set is waiting but frames are passed / pageable frames
+    from monocular_visual_odometry_va4mr_b200._lib import B200VOError
+    with pytest.raises(B200VOError):
+        sb.step(None, wl.lm_pts[0], wl.lm_obj[0], wl.n_lm[0], wl.cand_pts[0], wl.n_cand[0])
+    with pytest.raises(B200VOError):
+        sb.submit_frames(np.ascontiguousarray(wl.frames[0]))
+    sb.submit_frames(frames[0])
+    with pytest.raises(B200VOError):
+        sb.step(frames[1], wl.lm_pts[0], wl.lm_obj[0], wl.n_lm[0], wl.cand_pts[0], wl.n_cand[0])
+    sb.close()
