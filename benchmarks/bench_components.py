@@ -2,7 +2,7 @@
 """Secondary workloads of BASELINE.json (configs 2-4): per call-site timings through the C-ABI
 (host buffers in, host buffers out) next to the same cv2 call on the host cores.
 
-  python benchmarks/bench_components.py [--only knn,gftt,klt,pnp] [--reps 20]
+  python benchmarks/bench_components.py [--only knn,gftt,klt,pnp,emat] [--reps 20]
 
 Prints one JSON object per workload.  `gpu_ms` is CUDA-event time on the ctx stream for the whole
 call (H2D + kernels + D2H), `wall_ms` the median wall clock of the call, `cv2_ms` the median wall
@@ -34,13 +34,13 @@ def med(f, reps, warm=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="knn,gftt,klt,pnp")
+    ap.add_argument("--only", default="knn,gftt,klt,pnp,emat")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--no-cv2", action="store_true")
     args = ap.parse_args()
     only = set(args.only.split(","))
     from monocular_visual_odometry_va4mr_b200 import _lib, cv2_compat, synth
-    from make_golden import make_pnp_case, sift_like
+    from make_golden import make_emat_pair, make_pnp_case, sift_like
     cv2 = None
     if not args.no_cv2:
         try:
@@ -90,6 +90,14 @@ def main():
             r = {"workload": f"solvePnPRansac P3P N={n} outliers={of} iters<={iters}", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
             if cv2 is not None:
                 r["cv2_ms"] = med(lambda: cv2.solvePnPRansac(obj, img, K, np.zeros(4), **kw), 5, 1)
+            print(json.dumps(r))
+    if "emat" in only:   # bootstrap pose (config 3 tail): findEssentialMat(RANSAC, prob=0.99, threshold=1) as :308
+        for n, of in ((2500, 0.2), (3000, 0.4), (500, 0.6)):
+            p1, p2, K = make_emat_pair(n, of, 11)
+            wall = med(lambda: cv2_compat.findEssentialMat(p1, p2, K, method=cv2_compat.RANSAC, prob=0.99, threshold=1), args.reps)
+            r = {"workload": f"findEssentialMat RANSAC N={n} outliers={of}", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
+            if cv2 is not None:
+                r["cv2_ms"] = med(lambda: cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.99, threshold=1), 5, 1)
             print(json.dumps(r))
 
 

@@ -2,12 +2,13 @@
 // threshold) at reference VisualOdometryPipeLine.py:308; spec SURVEY.md A.6/A.7 and the header of
 // oracle/emat_oracle.c).
 //
-// All maxIters 5-subsets are drawn (bit-exact cv::RNG stream), solved and scored at once:
+// All maxIters 5-subsets are drawn (bit-exact cv::RNG stream) and solved at once; scoring goes in chunks:
 //   emat_normalize_kernel   pixels -> normalised double coordinates
 //   ransac_samples_kernel<5> (ransac.cuh)
-//   emat_solve_kernel       one thread per sample: Nister five-point in FP64 (Householder null
-//                           space, cubic constraints by polynomial arithmetic, Gauss-Jordan,
-//                           det B(z), Aberth roots, back-substitution) -> up to 10 models
+//   emat_solve_kernel       one WARP per sample: Nister five-point in FP64 (Householder null
+//                           space, cubic constraints with one monomial per lane, Gauss-Jordan
+//                           with one column per lane, det B(z), Aberth roots with one root per
+//                           lane, back-substitution) -> up to 10 models
 //   emat_score_kernel       (256 points) x (8 samples x <=10 models): Sampson error in double ->
 //                           float32, ballot+popc counts, one atomicAdd per warp
 //   emat_update_kernel      sequential replay of cv2's loop over (sample, model) counts with the
@@ -22,277 +23,364 @@ using namespace vo;
 
 #define EM_MAXM 10
 
-__constant__ signed char EM_TAB[20][20] = {
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 0},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 1},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 2},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 3},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 4},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 0,-1,-1, 2,-1,-1, 4, 5},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 6},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 3,-1,-1, 1,-1,-1, 6, 7},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 8},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 2,-1,-1, 3,-1,-1, 8, 9},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,10},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 4,-1,-1, 8,-1,-1,10,11},
-    {-1,-1,-1,-1,-1, 0,-1, 3,-1, 2,-1, 4, 5,-1, 8, 9,-1,10,11,12},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,13},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 8,-1,-1, 6,-1,-1,13,14},
-    {-1,-1,-1,-1,-1, 2,-1, 1,-1, 3,-1, 8, 9,-1, 6, 7,-1,13,14,15},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,16},
-    {-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,10,-1,-1,13,-1,-1,16,17},
-    {-1,-1,-1,-1,-1, 4,-1, 6,-1, 8,-1,10,11,-1,13,14,-1,16,17,18},
-    { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9,10,11,12,13,14,15,16,17,18,19}};
-// monomial indices of x, y, z, 1 in the ordering [x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1]
-#define EM_IX 12
-#define EM_IY 15
-#define EM_IZ 18
-#define EM_I1 19
+// ------------------------------------------------------------------------------------------
+// Warp-cooperative Nister five-point solver: ONE WARP per 5-point sample.
+//   1. null space of the 5x9 epipolar matrix: Householder QR of its transpose in registers
+//      (every lane redundantly, statically indexed); lane c < 4 expands basis vector c.
+//   2. the 10 cubic constraints det(E) = 0, 2 E E^T E - tr(E E^T) E = 0 in the 20 monomials of
+//      (x, y, z, 1): lane m owns monomial m and sums the trilinear forms over the distinct
+//      orderings of its basis triple -> column m of the 10 x 20 coefficient matrix, in registers.
+//   3. Gauss-Jordan with partial pivoting: lane = column, pivot column broadcast by shuffles.
+//   4. B(z) and the degree-10 determinant polynomial (every lane, registers).
+//   5. Aberth-Ehrlich iteration: lane k owns root k, the other roots arrive by shuffles.
+//   6. lane k polishes a real root (Newton), back-substitutes x, y and writes its E at the slot
+//      given by the ascending-z rank among the valid candidates.
+// Monomial order [x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1]; basis index
+// x = 0, y = 1, z = 2, 1 = 3.
+// ------------------------------------------------------------------------------------------
+#define EMW_WARPS 4
+struct EmwShared { double N[4][9]; double T[6][10]; };
 
-struct Poly { double c[20]; };
+__constant__ unsigned char EMW_TRI[20][3] = {
+    {0, 0, 0}, {1, 1, 1}, {0, 0, 1}, {0, 1, 1}, {0, 0, 2}, {0, 0, 3}, {1, 1, 2}, {1, 1, 3}, {0, 1, 2}, {0, 1, 3},
+    {0, 2, 2}, {0, 2, 3}, {0, 3, 3}, {1, 2, 2}, {1, 2, 3}, {1, 3, 3}, {2, 2, 2}, {2, 2, 3}, {2, 3, 3}, {3, 3, 3}};
 
-// Products only ever pair (degree <= 1) x (degree <= 1) and (degree <= 2) x (degree <= 1): iterate
-// over the 4 linear and 10 quadratic-or-lower monomials instead of all 20 x 20 pairs.
-__constant__ signed char EM_LIN[4] = {12, 15, 18, 19};
-__constant__ signed char EM_QUAD[10] = {5, 7, 9, 11, 12, 14, 15, 17, 18, 19};
-template <int NA>
-__device__ inline void pmul_n(const Poly& a, const Poly& b, Poly& o)
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double warp_max_d(double v)
 {
-    for (int i = 0; i < 20; ++i) o.c[i] = 0;
-    for (int ii = 0; ii < NA; ++ii) {
-        const int i = NA == 4 ? EM_LIN[ii] : EM_QUAD[ii];
-        const double ai = a.c[i];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int j = EM_LIN[jj];
-            o.c[EM_TAB[i][j]] += ai * b.c[j];
-        }
-    }
-}
-#define pmul_ll(a, b, o) pmul_n<4>(a, b, o)    /* linear x linear */
-#define pmul_ql(a, b, o) pmul_n<10>(a, b, o)   /* quadratic x linear */
-__device__ inline void paxpy(Poly& y, const Poly& x, double s)
-{
-    for (int i = 0; i < 20; ++i) y.c[i] += s * x.c[i];
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
-__device__ inline void poly1_mul(const double* a, int na, const double* b, int nb, double* o)
+// reciprocal to ~1 ulp for normal-range arguments: hardware seed + two Newton steps (no slow path)
+__device__ __forceinline__ double fast_rcp(double x)
 {
-    for (int i = 0; i <= na + nb; ++i) o[i] = 0;
-    for (int i = 0; i <= na; ++i)
-        for (int j = 0; j <= nb; ++j) o[i + j] += a[i] * b[j];
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return isfinite(r) && r != 0 ? r : 1.0 / x;
 }
 
-// all complex roots of c[0] + .. + c[n] z^n by Aberth-Ehrlich iteration
-__device__ inline int poly_roots(const double* c, int n, double* re, double* im)
+template <int NA, int NB>
+__device__ __forceinline__ void poly1_mul(const double* a, const double* b, double* o)
 {
-    while (n > 0 && c[n] == 0) --n;
-    if (n <= 0) return 0;
-    double a[11];
-    for (int i = 0; i <= n; ++i) a[i] = c[i] / c[n];
-    double rad = 0;   // Fujiwara-style root bound: max |a_i|^(1/(n-i))
-    for (int i = 0; i < n; ++i) if (a[i] != 0) rad = fmax(rad, pow(fabs(a[i]), 1.0 / (n - i)));
-    if (!isfinite(rad)) return 0;
-    rad = rad > 0 ? 0.7 * rad : 1.0;
-    for (int k = 0; k < n; ++k) {
-        const double ang = 6.283185307179586476925286766559 * k / n + 0.4, r = rad * (1 + 0.1 * k / n);
-        re[k] = r * cos(ang); im[k] = r * sin(ang);
-    }
-    for (int it = 0; it < 200; ++it) {
-        double maxstep = 0;
-        for (int k = 0; k < n; ++k) {
-            double pr = 1, pi = 0, dr = 0, di = 0;
-            const double zr = re[k], zi = im[k];
-            for (int i = n - 1; i >= 0; --i) {
-                const double ndr = dr * zr - di * zi + pr, ndi = dr * zi + di * zr + pi;
-                const double npr = pr * zr - pi * zi + a[i], npi = pr * zi + pi * zr;
-                dr = ndr; di = ndi; pr = npr; pi = npi;
-            }
-            const double den = dr * dr + di * di;
-            if (den == 0) continue;
-            const double wr = (pr * dr + pi * di) / den, wi = (pi * dr - pr * di) / den;
-            double sr = 0, si = 0;
-            for (int j = 0; j < n; ++j) {
-                if (j == k) continue;
-                const double er = zr - re[j], ei = zi - im[j], d2 = er * er + ei * ei;
-                if (d2 == 0) continue;
-                sr += er / d2; si -= ei / d2;
-            }
-            const double qr = 1 - (wr * sr - wi * si), qi = -(wr * si + wi * sr);
-            const double qd = qr * qr + qi * qi;
-            if (qd == 0) continue;
-            const double stepr = (wr * qr + wi * qi) / qd, stepi = (wi * qr - wr * qi) / qd;
-            re[k] -= stepr; im[k] -= stepi;
-            const double st = fabs(stepr) + fabs(stepi), sc = fabs(re[k]) + fabs(im[k]) + 1e-300;
-            maxstep = fmax(maxstep, st / sc);
-        }
-        if (maxstep < 1e-12) break;   // real roots are Newton-polished afterwards
-    }
-    return n;
+#pragma unroll
+    for (int i = 0; i <= NA + NB; ++i) o[i] = 0;
+#pragma unroll
+    for (int i = 0; i <= NA; ++i)
+#pragma unroll
+        for (int j = 0; j <= NB; ++j) o[i + j] += a[i] * b[j];
 }
 
-// x1, x2: 5 normalised correspondences; E: up to 10 row-major models with unit Frobenius norm
-__device__ int five_point(const double* x1, const double* x2, double (*E)[9])
+// step 1; returns false for a rank-deficient sample (warp-uniform)
+__device__ __forceinline__ bool emw_null_space(const double* s1, const double* s2, int lane, double (*Nsm)[9])
 {
-    // ---- null space of the 5x9 epipolar matrix by Householder QR of its transpose ----
-    double A9[9][5], V[5][9], beta[5], N[4][9];
+    double A[9][5], V[5][9], beta[5];
+#pragma unroll
     for (int i = 0; i < 5; ++i) {
-        const double a = x1[2 * i], b = x1[2 * i + 1], c = x2[2 * i], d = x2[2 * i + 1];
+        const double a = s1[2 * i], b = s1[2 * i + 1], c = s2[2 * i], d = s2[2 * i + 1];
         const double r[9] = {c * a, c * b, c, d * a, d * b, d, a, b, 1.0};
-        for (int j = 0; j < 9; ++j) A9[j][i] = r[j];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) A[j][i] = r[j];
     }
+    bool ok = true;
+#pragma unroll
     for (int k = 0; k < 5; ++k) {
         double nrm = 0;
-        for (int i = k; i < 9; ++i) nrm += A9[i][k] * A9[i][k];
+#pragma unroll
+        for (int i = k; i < 9; ++i) nrm += A[i][k] * A[i][k];
         nrm = sqrt(nrm);
-        if (nrm < 1e-300) return 0;
-        const double alpha = A9[k][k] > 0 ? -nrm : nrm;
-        for (int i = 0; i < 9; ++i) V[k][i] = i < k ? 0 : A9[i][k];
+        if (nrm < 1e-300) ok = false;
+        const double alpha = A[k][k] > 0 ? -nrm : nrm;
+#pragma unroll
+        for (int i = k; i < 9; ++i) V[k][i] = A[i][k];
         V[k][k] -= alpha;
         double vn = 0;
+#pragma unroll
         for (int i = k; i < 9; ++i) vn += V[k][i] * V[k][i];
         beta[k] = vn > 0 ? 2 / vn : 0;
+#pragma unroll
         for (int j = k; j < 5; ++j) {
-            double s = 0;
-            for (int i = k; i < 9; ++i) s += V[k][i] * A9[i][j];
-            s *= beta[k];
-            for (int i = k; i < 9; ++i) A9[i][j] -= s * V[k][i];
+            double sdot = 0;
+#pragma unroll
+            for (int i = k; i < 9; ++i) sdot += V[k][i] * A[i][j];
+            sdot *= beta[k];
+#pragma unroll
+            for (int i = k; i < 9; ++i) A[i][j] -= sdot * V[k][i];
         }
     }
-    for (int c = 0; c < 4; ++c) {
-        double e[9];
-        for (int i = 0; i < 9; ++i) e[i] = (i == 5 + c) ? 1.0 : 0.0;
-        for (int k = 4; k >= 0; --k) {
-            double s = 0;
-            for (int i = k; i < 9; ++i) s += V[k][i] * e[i];
-            s *= beta[k];
-            for (int i = k; i < 9; ++i) e[i] -= s * V[k][i];
-        }
-        for (int i = 0; i < 9; ++i) N[c][i] = e[i];
+    double e[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) e[i] = (i == 5 + (lane & 3)) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+        double sdot = 0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) sdot += V[k][i] * e[i];
+        sdot *= beta[k];
+#pragma unroll
+        for (int i = k; i < 9; ++i) e[i] -= sdot * V[k][i];
     }
-    // ---- ten cubic constraints ----
-    Poly Ep[3][3], t1, t2;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            for (int k = 0; k < 20; ++k) Ep[i][j].c[k] = 0;
-            Ep[i][j].c[EM_IX] = N[0][3 * i + j]; Ep[i][j].c[EM_IY] = N[1][3 * i + j];
-            Ep[i][j].c[EM_IZ] = N[2][3 * i + j]; Ep[i][j].c[EM_I1] = N[3][3 * i + j];
-        }
-    double A[10][20];
+    if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Nsm[lane][i] = e[i];
+    }
+    return ok;
+}
+
+// whole solver; every lane of the warp calls it.  Writes up to 10 unit-norm models (row-major) to
+// `models` in ascending-z order and returns their number (warp-uniform).
+__device__ int five_point_warp(const double* s1, const double* s2, EmwShared& S, int lane, double* models)
+{
+    if (!emw_null_space(s1, s2, lane, S.N)) return 0;
+    __syncwarp();
+    // ---- 2. this lane's column of the constraint matrix ----
+    double col[10];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) col[r] = 0;
     {
-        Poly acc;
-        for (int k = 0; k < 20; ++k) acc.c[k] = 0;
-        const int perm[6][4] = {{0, 1, 2, 1}, {1, 2, 0, 1}, {2, 0, 1, 1}, {2, 1, 0, -1}, {1, 0, 2, -1}, {0, 2, 1, -1}};
+        const int m = lane < 20 ? lane : 19;
+        const int t[3] = {EMW_TRI[m][0], EMW_TRI[m][1], EMW_TRI[m][2]};
+        const int P[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+        int pa[6], pb[6], pc[6];
+        bool inc[6];
+#pragma unroll
         for (int p = 0; p < 6; ++p) {
-            pmul_ll(Ep[0][perm[p][0]], Ep[1][perm[p][1]], t1);
-            pmul_ql(t1, Ep[2][perm[p][2]], t2);
-            paxpy(acc, t2, (double)perm[p][3]);
+            pa[p] = t[P[p][0]]; pb[p] = t[P[p][1]]; pc[p] = t[P[p][2]];
+            inc[p] = true;
+#pragma unroll
+            for (int q = 0; q < p; ++q) if (pa[q] == pa[p] && pb[q] == pb[p] && pc[q] == pc[p]) inc[p] = false;
         }
-        for (int k = 0; k < 20; ++k) A[0][k] = acc.c[k];
+#pragma unroll 1
+        for (int p = 0; p < 6; ++p) {
+            int ia = pa[0], ib = pb[0], ic = pc[0];
+            bool on = inc[0];
+#pragma unroll
+            for (int q = 1; q < 6; ++q) if (p == q) { ia = pa[q]; ib = pb[q]; ic = pc[q]; on = inc[q]; }
+            const double* A = S.N[ia];
+            const double* B = S.N[ib];
+            const double* C = S.N[ic];
+            double a[9], b[9], c[9], M[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { a[i] = A[i]; b[i] = B[i]; c[i] = C[i]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) M[3 * r + q] = a[3 * r] * b[3 * q] + a[3 * r + 1] * b[3 * q + 1] + a[3 * r + 2] * b[3 * q + 2];
+            const double tr = M[0] + M[4] + M[8];
+            const double w = on ? 1.0 : 0.0;
+            // det: row 0 of A . (row 1 of B x row 2 of C)
+            const double cx = b[4] * c[8] - b[5] * c[7], cy = b[5] * c[6] - b[3] * c[8], cz = b[3] * c[7] - b[4] * c[6];
+            col[0] += w * (a[0] * cx + a[1] * cy + a[2] * cz);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const double mc = M[3 * r] * c[q] + M[3 * r + 1] * c[3 + q] + M[3 * r + 2] * c[6 + q];
+                    col[1 + 3 * r + q] += w * (2.0 * mc - tr * c[3 * r + q]);
+                }
+        }
     }
-    {
-        Poly EEt[3][3], tr;
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                for (int k = 0; k < 20; ++k) EEt[i][j].c[k] = 0;
-                for (int k = 0; k < 3; ++k) { pmul_ll(Ep[i][k], Ep[j][k], t1); paxpy(EEt[i][j], t1, 1.0); }
-            }
-        for (int k = 0; k < 20; ++k) tr.c[k] = EEt[0][0].c[k] + EEt[1][1].c[k] + EEt[2][2].c[k];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                Poly acc;
-                for (int k = 0; k < 20; ++k) acc.c[k] = 0;
-                for (int k = 0; k < 3; ++k) { pmul_ql(EEt[i][k], Ep[k][j], t1); paxpy(acc, t1, 2.0); }
-                pmul_ql(tr, Ep[i][j], t1);
-                paxpy(acc, t1, -1.0);
-                for (int k = 0; k < 20; ++k) A[1 + 3 * i + j][k] = acc.c[k];
-            }
-    }
-    // ---- Gauss-Jordan (partial pivoting) on the first ten columns ----
+    // ---- 3. Gauss-Jordan, lane = column ----
+    bool ok = true;
+#pragma unroll
     for (int c = 0; c < 10; ++c) {
+        double f[10];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) f[r] = shfl_d(col[r], c);
         int piv = c;
-        for (int r = c + 1; r < 10; ++r) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
-        if (fabs(A[piv][c]) < 1e-300) return 0;
-        if (piv != c) for (int k = 0; k < 20; ++k) { const double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
-        const double inv = 1.0 / A[c][c];
-        for (int k = 0; k < 20; ++k) A[c][k] *= inv;
-        for (int r = 0; r < 10; ++r) {
-            if (r == c) continue;
-            const double f = A[r][c];
-            if (f == 0) continue;
-            for (int k = 0; k < 20; ++k) A[r][k] -= f * A[c][k];
-        }
+        double best = fabs(f[c]);
+#pragma unroll
+        for (int r = c + 1; r < 10; ++r) if (fabs(f[r]) > best) { best = fabs(f[r]); piv = r; }
+        if (best < 1e-300) ok = false;
+#pragma unroll
+        for (int r = c + 1; r < 10; ++r)
+            if (piv == r) {
+                const double t0 = col[c]; col[c] = col[r]; col[r] = t0;
+                const double t1 = f[c]; f[c] = f[r]; f[r] = t1;
+            }
+        const double inv = 1.0 / f[c];
+        col[c] *= inv;
+#pragma unroll
+        for (int r = 0; r < 10; ++r)
+            if (r != c) col[r] -= f[r] * col[c];
     }
-    // ---- B(z) and its determinant ----
+    if (!ok) return 0;
+    // ---- 4. B(z), det B(z) ----
+    __syncwarp();
+    if (lane >= 10 && lane < 20) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) S.T[r][lane - 10] = col[4 + r];
+    }
+    __syncwarp();
     double Bx[3][4], By[3][4], Bc[3][5];
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const double* r1 = A[2 * i + 4] + 10;
-        const double* r2 = A[2 * i + 5] + 10;
+        const double* r1 = S.T[2 * i];
+        const double* r2 = S.T[2 * i + 1];
         Bx[i][3] = -r2[0]; Bx[i][2] = r1[0] - r2[1]; Bx[i][1] = r1[1] - r2[2]; Bx[i][0] = r1[2];
         By[i][3] = -r2[3]; By[i][2] = r1[3] - r2[4]; By[i][1] = r1[4] - r2[5]; By[i][0] = r1[5];
         Bc[i][4] = -r2[6]; Bc[i][3] = r1[6] - r2[7]; Bc[i][2] = r1[7] - r2[8]; Bc[i][1] = r1[8] - r2[9]; Bc[i][0] = r1[9];
     }
-    double det[11], m1[8], m2[8], m3[11], m4[7], m5[7];
-    for (int k = 0; k < 11; ++k) det[k] = 0;
-    poly1_mul(By[1], 3, Bc[2], 4, m1); poly1_mul(Bc[1], 4, By[2], 3, m2);
-    for (int k = 0; k < 8; ++k) m1[k] -= m2[k];
-    poly1_mul(Bx[0], 3, m1, 7, m3);
-    for (int k = 0; k < 11; ++k) det[k] += m3[k];
-    poly1_mul(Bx[1], 3, Bc[2], 4, m1); poly1_mul(Bc[1], 4, Bx[2], 3, m2);
-    for (int k = 0; k < 8; ++k) m1[k] -= m2[k];
-    poly1_mul(By[0], 3, m1, 7, m3);
-    for (int k = 0; k < 11; ++k) det[k] -= m3[k];
-    poly1_mul(Bx[1], 3, By[2], 3, m4); poly1_mul(By[1], 3, Bx[2], 3, m5);
-    for (int k = 0; k < 7; ++k) m4[k] -= m5[k];
-    poly1_mul(Bc[0], 4, m4, 6, m3);
-    for (int k = 0; k < 11; ++k) det[k] += m3[k];
-    double rr[10], ri[10], zs[10];
-    const int nroots = poly_roots(det, 10, rr, ri);
-    int nz = 0;
-    for (int k = 0; k < nroots; ++k) {
-        if (!(fabs(ri[k]) <= 1e-10)) continue;
-        double z = rr[k];
-        for (int it = 0; it < 2; ++it) {
+    double det[11];
+    {
+        double m1[8], m2[8], m3[11], m4[7], m5[7];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) det[k] = 0;
+        poly1_mul<3, 4>(By[1], Bc[2], m1); poly1_mul<4, 3>(Bc[1], By[2], m2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m1[k] -= m2[k];
+        poly1_mul<3, 7>(Bx[0], m1, m3);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) det[k] += m3[k];
+        poly1_mul<3, 4>(Bx[1], Bc[2], m1); poly1_mul<4, 3>(Bc[1], Bx[2], m2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m1[k] -= m2[k];
+        poly1_mul<3, 7>(By[0], m1, m3);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) det[k] -= m3[k];
+        poly1_mul<3, 3>(Bx[1], By[2], m4); poly1_mul<3, 3>(By[1], Bx[2], m5);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) m4[k] -= m5[k];
+        poly1_mul<4, 6>(Bc[0], m4, m3);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) det[k] += m3[k];
+    }
+    // ---- 5. all complex roots: Aberth-Ehrlich, lane k = root k ----
+    int n = 10;
+#pragma unroll
+    for (int i = 10; i >= 1; --i) if (n == i && det[i] == 0) n = i - 1;
+    if (n <= 0) return 0;
+    double lead = det[10];
+#pragma unroll
+    for (int i = 9; i >= 1; --i) if (n == i) lead = det[i];
+    double am[10];   // monic coefficients a_0 .. a_{n-1}
+#pragma unroll
+    for (int i = 0; i < 10; ++i) am[i] = det[i] / lead;
+    double mine = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) if (lane == i) mine = am[i];
+    double rad = (lane < n && mine != 0) ? pow(fabs(mine), 1.0 / (n - lane)) : 0.0;
+    {
+        const bool bad = __any_sync(0xffffffffu, !isfinite(rad));
+        if (bad) return 0;
+    }
+    rad = warp_max_d(rad);
+    rad = rad > 0 ? 0.7 * rad : 1.0;
+    double zr, zi;
+    {
+        const int k = lane < n ? lane : 0;
+        const double ang = 6.283185307179586476925286766559 * k / n + 0.4, r = rad * (1 + 0.1 * k / n);
+        zr = r * cos(ang); zi = r * sin(ang);
+    }
+    const bool mineroot = lane < n;
+    // (fused multiply-adds and Newton reciprocals in this loop: the iterates are self-correcting, and
+    // the real roots are polished against the exact coefficients afterwards)
+    for (int it = 0; it < 200; ++it) {
+        double pr = 1, pi = 0, dr = 0, di = 0, sb = 1;
+        const double az = sqrt(fma(zr, zr, zi * zi));
+#pragma unroll
+        for (int i = 9; i >= 0; --i) {
+            if (i < n) {
+                const double ndr = fma(dr, zr, fma(-di, zi, pr)), ndi = fma(dr, zi, fma(di, zr, pi));
+                const double npr = fma(pr, zr, fma(-pi, zi, am[i])), npi = fma(pr, zi, pi * zr);
+                dr = ndr; di = ndi; pr = npr; pi = npi;
+                sb = fma(sb, az, fabs(am[i]));          // sum |a_i| |z|^i: scale of the rounding error of p(z)
+            }
+        }
+        double sr = 0, si = 0;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const double ojr = shfl_d(zr, j), oji = shfl_d(zi, j);
+            if (j < n && j != lane) {
+                const double er = zr - ojr, ei = zi - oji, d2 = fma(er, er, ei * ei);
+                if (d2 != 0) { const double id2 = fast_rcp(d2); sr = fma(er, id2, sr); si = fma(-ei, id2, si); }
+            }
+        }
+        double rel = 0;
+        const double den = fma(dr, dr, di * di);
+        if (mineroot && den != 0) {
+            const double iden = fast_rcp(den);
+            const double wr = fma(pr, dr, pi * di) * iden, wi = fma(pi, dr, -pr * di) * iden;
+            const double qr = 1 - fma(wr, sr, -wi * si), qi = -fma(wr, si, wi * sr);
+            const double qd = fma(qr, qr, qi * qi);
+            if (qd != 0) {
+                const double iqd = fast_rcp(qd);
+                const double stepr = fma(wr, qr, wi * qi) * iqd, stepi = fma(wi, qr, -wr * qi) * iqd;
+                zr -= stepr; zi -= stepi;
+                rel = (fabs(stepr) + fabs(stepi)) / (fabs(zr) + fabs(zi) + 1e-300);
+            }
+        }
+        // A root is settled when its step is below 1e-12 (relative); when |p(z)| has reached the
+        // rounding noise of its own evaluation (an ill-conditioned root cannot get closer); or --
+        // only real roots become models -- when it is unmistakably complex and within 1e-6 of its
+        // limit (close complex clusters converge linearly and would keep the whole warp iterating).
+        const double mag = fabs(zr) + fabs(zi);
+        const bool noise = fabs(pr) + fabs(pi) <= 2e-14 * sb;
+        const bool settled = !mineroot || rel < 1e-12 || noise ||
+                             (it >= 8 && rel < 1e-6 && fabs(zi) > 1e-4 * mag && fabs(zi) > 1e-7);
+        if (__all_sync(0xffffffffu, settled)) break;   // real roots are Newton-polished below
+    }
+    // ---- 6. real roots -> models ----
+    bool cand = mineroot && fabs(zi) <= 1e-10;
+    double z = zr;
+    if (cand) {
+#pragma unroll 1
+        for (int itn = 0; itn < 2; ++itn) {
             double p = det[10], dp = 0;
+#pragma unroll
             for (int i = 9; i >= 0; --i) { dp = dp * z + p; p = p * z + det[i]; }
             if (dp != 0 && isfinite(p / dp)) z -= p / dp;
         }
-        zs[nz++] = z;
     }
-    for (int i = 1; i < nz; ++i) {   // ascending z: deterministic candidate order
-        const double v = zs[i];
-        int j = i - 1;
-        while (j >= 0 && zs[j] > v) { zs[j + 1] = zs[j]; --j; }
-        zs[j + 1] = v;
-    }
-    int count = 0;
-    for (int k = 0; k < nz; ++k) {
-        const double z = zs[k];
+    double Ev[9];
+    bool valid = false;
+    if (cand) {
         double Bz[3][3];
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
             Bz[i][0] = ((Bx[i][3] * z + Bx[i][2]) * z + Bx[i][1]) * z + Bx[i][0];
             Bz[i][1] = ((By[i][3] * z + By[i][2]) * z + By[i][1]) * z + By[i][0];
             Bz[i][2] = (((Bc[i][4] * z + Bc[i][3]) * z + Bc[i][2]) * z + Bc[i][1]) * z + Bc[i][0];
         }
         double best[3] = {0, 0, 0}, bn = -1;
+#pragma unroll
         for (int a = 0; a < 3; ++a)
+#pragma unroll
             for (int b = a + 1; b < 3; ++b) {
-                const double c[3] = {Bz[a][1] * Bz[b][2] - Bz[a][2] * Bz[b][1], Bz[a][2] * Bz[b][0] - Bz[a][0] * Bz[b][2],
-                                     Bz[a][0] * Bz[b][1] - Bz[a][1] * Bz[b][0]};
-                const double n2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
-                if (n2 > bn) { bn = n2; best[0] = c[0]; best[1] = c[1]; best[2] = c[2]; }
+                const double c0 = Bz[a][1] * Bz[b][2] - Bz[a][2] * Bz[b][1], c1 = Bz[a][2] * Bz[b][0] - Bz[a][0] * Bz[b][2],
+                             c2 = Bz[a][0] * Bz[b][1] - Bz[a][1] * Bz[b][0];
+                const double n2 = c0 * c0 + c1 * c1 + c2 * c2;
+                if (n2 > bn) { bn = n2; best[0] = c0; best[1] = c1; best[2] = c2; }
             }
-        if (!(bn > 0)) continue;
-        if (fabs(best[2] / sqrt(bn)) < 1e-10) continue;
-        const double x = best[0] / best[2], y = best[1] / best[2];
-        double Ev[9], nrm = 0;
-        for (int i = 0; i < 9; ++i) { Ev[i] = x * N[0][i] + y * N[1][i] + z * N[2][i] + N[3][i]; nrm += Ev[i] * Ev[i]; }
-        nrm = sqrt(nrm);
-        if (!(nrm > 0) || !isfinite(nrm)) continue;
-        for (int i = 0; i < 9; ++i) E[count][i] = Ev[i] / nrm;
-        ++count;
+        if (bn > 0 && !(fabs(best[2] / sqrt(bn)) < 1e-10)) {
+            const double x = best[0] / best[2], y = best[1] / best[2];
+            double nrm = 0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { Ev[i] = x * S.N[0][i] + y * S.N[1][i] + z * S.N[2][i] + S.N[3][i]; nrm += Ev[i] * Ev[i]; }
+            nrm = sqrt(nrm);
+            if (nrm > 0 && isfinite(nrm)) {
+                valid = true;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Ev[i] /= nrm;
+            }
+        }
     }
-    return count;
+    // ascending z among the valid candidates (ties: lower root index first)
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    int slot = 0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const double zj = shfl_d(z, j);
+        if (((vmask >> j) & 1u) && (zj < z || (zj == z && j < lane))) ++slot;
+    }
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) models[slot * 9 + i] = Ev[i];
+    }
+    return __popc(vmask);
 }
 
 struct EmatArgs {
@@ -323,27 +411,25 @@ emat_normalize_kernel(EmatArgs a)
     a.x2[2 * i] = ((double)a.p2[2 * i] - a.cx) / a.fx; a.x2[2 * i + 1] = ((double)a.p2[2 * i + 1] - a.cy) / a.fy;
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(EMW_WARPS * 32)
 emat_solve_kernel(EmatArgs a)
 {
-    if (a.chunk_start >= a.state[0]) return;   // cv2's adaptive bound was reached in an earlier chunk
-    const int it = a.chunk_start + blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= a.iters || it >= a.chunk_start + a.chunk_len) return;
-    for (int m = 0; m < EM_MAXM; ++m) a.counts[it * EM_MAXM + m] = 0;
-    a.nmodels[it] = 0;
+    __shared__ EmwShared sh[EMW_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int it = blockIdx.x * EMW_WARPS + warp;
+    if (it >= a.iters) return;
+    if (lane < EM_MAXM) a.counts[it * EM_MAXM + lane] = 0;
     const int* smp = a.samples + 5 * it;
-    if (smp[0] < 0) return;
+    if (smp[0] < 0) { if (lane == 0) a.nmodels[it] = 0; return; }
     double s1[10], s2[10];
+#pragma unroll
     for (int k = 0; k < 5; ++k) {
         const int s = smp[k];
         s1[2 * k] = a.x1[2 * s]; s1[2 * k + 1] = a.x1[2 * s + 1];
         s2[2 * k] = a.x2[2 * s]; s2[2 * k + 1] = a.x2[2 * s + 1];
     }
-    double E[EM_MAXM][9];
-    const int nm = five_point(s1, s2, E);
-    for (int m = 0; m < nm; ++m)
-        for (int k = 0; k < 9; ++k) a.models[((size_t)it * EM_MAXM + m) * 9 + k] = E[m][k];
-    a.nmodels[it] = nm;
+    const int nm = five_point_warp(s1, s2, sh[warp], lane, a.models + (size_t)it * EM_MAXM * 9);
+    if (lane == 0) a.nmodels[it] = nm;
 }
 
 __device__ __forceinline__ bool sampson_inlier(const double* E, double ax, double ay, double bx, double by, float thr_sq)
@@ -483,12 +569,15 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
     // iteration bound (known on the device after the previous chunk) exits immediately
     const int CH = 128;
     ctx->launches += 2;
+    // every sample is solved up front: one warp each, so the launch is one wave of latency-bound warps
+    // whether it carries 128 samples or all of them
+    emat_solve_kernel<<<(iters + EMW_WARPS - 1) / EMW_WARPS, EMW_WARPS * 32, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
     for (int c0 = 0; c0 < iters; c0 += CH) {
         a.chunk_start = c0; a.chunk_len = CH;
-        emat_solve_kernel<<<(CH + 31) / 32, 32, 0, ctx->stream>>>(a);
         emat_score_kernel<<<dim3((n + 255) / 256, (CH + EM_ST - 1) / EM_ST), 256, 0, ctx->stream>>>(a);
         emat_update_kernel<<<1, 32, 0, ctx->stream>>>(a);
-        ctx->launches += 3;
+        ctx->launches += 2;
     }
     emat_finish_kernel<<<1, 256, 0, ctx->stream>>>(a);
     ctx->launches += 1;
