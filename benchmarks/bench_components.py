@@ -2,7 +2,7 @@
 """Secondary workloads of BASELINE.json (configs 2-4): per call-site timings through the C-ABI
 (host buffers in, host buffers out) next to the same cv2 call on the host cores.
 
-  python benchmarks/bench_components.py [--only knn,gftt,klt,pnp,emat] [--reps 20]
+  python benchmarks/bench_components.py [--only knn,gftt,klt,pnp,emat,next] [--reps 20]
 
 Prints one JSON object per workload.  `gpu_ms` is CUDA-event time on the ctx stream for the whole
 call (H2D + kernels + D2H), `wall_ms` the median wall clock of the call, `cv2_ms` the median wall
@@ -34,7 +34,7 @@ def med(f, reps, warm=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="knn,gftt,klt,pnp,emat")
+    ap.add_argument("--only", default="knn,gftt,klt,pnp,emat,next")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--no-cv2", action="store_true")
     args = ap.parse_args()
@@ -99,6 +99,40 @@ def main():
             if cv2 is not None:
                 r["cv2_ms"] = med(lambda: cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.99, threshold=1), 5, 1)
             print(json.dumps(r))
+    if "next" in only:   # candidate min-distance filter (:258) and triangulate_landmarks (:107-206)
+        from monocular_visual_odometry_va4mr_b200 import hotpath
+        rng = np.random.default_rng(3)
+        pts = np.rint(rng.uniform(0, 1241, (1400, 2))).astype(np.float32)
+        ex = (rng.uniform(0, 1, (1500, 2)) * [1241, 376]).astype(np.float32)
+        wall = med(lambda: hotpath.min_distance_mask(pts, ex, 10.0), args.reps)
+        r = {"workload": "candidate min-distance filter, 1400 corners x 1500 candidates (ref :258)", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
+        # the reference's own numpy expression, timed as the reference runs it (one Python iteration per corner)
+        r["numpy_ms"] = med(lambda: np.array([np.all(np.linalg.norm(pts[i, :] - ex, axis=1) > 10) for i in range(pts.shape[0])]), 3, 1)
+        print(json.dumps(r))
+        K = synth.K_KITTI
+        n = 1500
+        Xw = np.column_stack([rng.uniform(-8, 8, n), rng.uniform(-2, 1.6, n), rng.uniform(5, 120, n)])
+        R1, c1 = synth.Corridor.pose(3, 0.8)
+        p0 = synth.project(K, np.eye(3), np.zeros(3), Xw).astype(np.float32)
+        p1 = (synth.project(K, R1, c1, Xw) + rng.normal(0, 0.3, (n, 2))).astype(np.float32)
+        transforms = [(np.eye(3), np.zeros((3, 1))), (np.eye(3), np.zeros((3, 1))), (np.eye(3), np.zeros((3, 1)))]
+        opt = dict(min_dist_landmarks=1, max_dist_landmarks=150, min_baseline_angle=2, min_baseline_frames=2)
+        fp = np.zeros(n)
+        wall = med(lambda: hotpath.triangulate_landmarks(K, opt, p0, p1, fp, transforms, R1, c1.reshape(3, 1)), args.reps)
+        r = {"workload": f"triangulate_landmarks candidate loop, {n} candidates (ref :170-204)", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
+        if cv2 is not None:   # what the reference does per candidate: one cv2.triangulatePoints call + numpy gates
+            P0 = K @ np.hstack([np.eye(3), np.zeros((3, 1))])
+            P1 = K @ np.hstack([R1.T, (-R1.T @ c1).reshape(3, 1)])
+
+            def ref_loop():
+                out = []
+                for i in range(n):
+                    X = cv2.triangulatePoints(P0, P1, p0[i].reshape(-1, 1), p1[i].reshape(-1, 1))
+                    out.append(X[:3] / X[3])
+                return out
+            r["cv2_loop_ms"] = med(ref_loop, 3, 1)
+            r["note"] = "cv2_loop_ms covers only the per-candidate cv2.triangulatePoints calls of the reference's loop (no angle/depth gates)"
+        print(json.dumps(r))
 
 
 if __name__ == "__main__":

@@ -96,6 +96,35 @@ int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1, const flo
                                      double E[9], uint8_t* mask, int* found);
 
 /*
+ * ---- components next to the hot path ----
+ *
+ * Replaces the candidate min-distance filter of feature_adding at :258
+ *   valid_dist[i] = np.all(np.linalg.norm(pts[i,:] - self.potential_keys, axis=1) > min_dist)
+ * pts float32 (n,2) = the goodFeaturesToTrack corners, existing float32 (m,2) = potential_keys;
+ * valid uint8 (n).  float32 arithmetic rounded as numpy rounds it (m == 0: all valid).
+ */
+int b200vo_min_distance_mask(b200vo_ctx* ctx, const float* pts, int n, const float* existing, int m,
+                             float min_dist, uint8_t* valid);
+
+/*
+ * Replaces the per-candidate loop of triangulate_landmarks at :107-206: age gate (:171-174),
+ * bearing-angle gate check_baseline (:117-147), cv2.triangulatePoints (:188-193), float32
+ * de-homogenisation (:194) and the depth window disambguate_landmark (:149-168).
+ * first_keys / keys float32 (n,2) = potential_first_keys / potential_keys; first_pose int32 (n) =
+ * potential_transforms; poses_cw double (n_poses,12) = self.transforms as (R_CW row-major | t_CW),
+ * n_poses = len(self.transforms) at call time; cur_pose_cw = (R_current_CW | t_current_CW).
+ * too_short_baseline uint8 (n) is the mask the reference hands to filter_potential (:206);
+ * new_landmarks float32 (*n_new,3) / new_keypoints float32 (*n_new,2) are the rows it appends to
+ * matched_landmarks / matched_keypoints, in candidate order (caller provides room for n rows).
+ */
+int b200vo_triangulate_landmarks(b200vo_ctx* ctx, const double K[9], double min_dist, double max_dist,
+                                 double min_baseline_angle_deg, int min_baseline_frames,
+                                 const float* first_keys, const float* keys, const int32_t* first_pose,
+                                 int n, const double* poses_cw, int n_poses,
+                                 const double cur_pose_cw[12], uint8_t* too_short_baseline,
+                                 float* new_landmarks, float* new_keypoints, int* n_new);
+
+/*
  * Replaces cv2.solvePnPRansac(obj, img, K, zeros(4), flags=SOLVEPNP_P3P, confidence=,
  * reprojectionError=, iterationsCount=) at :343 (incl. cv2's EPnP refit on the inliers).
  * obj float32 (n,3), img float32 (n,2).  inliers int32 (n) caller-allocated, ascending,

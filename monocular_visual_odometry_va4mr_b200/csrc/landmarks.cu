@@ -1,0 +1,244 @@
+// The two components next to the hot path, downstream of the tracker and of
+// goodFeaturesToTrack in the reference's per-frame loop:
+//   f2  candidate min-distance filter, reference VisualOdometryPipeLine.py:258
+//         valid[i] = np.all(np.linalg.norm(pts[i,:] - self.potential_keys, axis=1) > min_dist)
+//       (float32: squares, sum and square root rounded as numpy rounds them);
+//   f1  triangulate_landmarks, reference :107-206: age gate (:171-174), bearing-angle gate
+//       (:117-147), cv2.triangulatePoints (:188-193: 4x4 DLT, OpenCV's small-matrix Jacobi SVD,
+//       float32 homogeneous output), de-homogenisation (:194), depth window in both cameras
+//       (:149-168); accepted landmarks and their keypoints appended in candidate order.
+// The reference spends ~67 ms (f1) and ~48 ms (f2) per frame on these in Python loops
+// (SURVEY.md 8f); here each is one or two small launches.
+#include "internal.cuh"
+#include "mathdev.cuh"
+
+using namespace vo;
+
+// ---- f2: one warp per new corner, lanes stride over the existing candidates ----
+__global__ void __launch_bounds__(256)
+min_distance_kernel(const float2* __restrict__ pts, int n, const float2* __restrict__ existing, int m, float min_dist,
+                    uint8_t* __restrict__ valid)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const float2 p = pts[i];
+    bool ok = true;
+    for (int j0 = 0; j0 < m; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < m) {
+            const float2 q = existing[j];
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y);
+            const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+            ok = d > min_dist;           // NaN compares false, as in numpy
+        }
+        if (!__all_sync(0xffffffffu, ok)) { ok = false; break; }
+    }
+    if (lane == 0) valid[i] = ok ? 1 : 0;
+}
+
+struct TriArgs {
+    double K[9], Ki[9];
+    double cur[12];            // R_CW | t_CW of the current frame (as the reference stores them)
+    double min_dist, max_dist, min_angle_deg;
+    int min_frames, n, n_poses;
+    const float* first_keys; const float* keys; const int* first_pose;
+    const double* poses;       // [n_poses][12]
+    uint8_t* keep;             // [n] too_short_baseline
+    float* lm_slot;            // [n][3] per-candidate result
+    float* out_lm; float* out_kp; int* n_new;   // compacted
+    int* flags;                // bit0: first_pose out of range
+};
+
+__device__ __forceinline__ void invert_pose(const double* cw, double* R, double* t)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = cw[3 * j + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = -(R[3 * i] * cw[9] + R[3 * i + 1] * cw[10] + R[3 * i + 2] * cw[11]);
+}
+__device__ __forceinline__ void proj_matrix(const double* K, const double* R, const double* t, double* P)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) P[4 * i + j] = K[3 * i] * R[j] + K[3 * i + 1] * R[3 + j] + K[3 * i + 2] * R[6 + j];
+        P[4 * i + 3] = K[3 * i] * t[0] + K[3 * i + 1] * t[1] + K[3 * i + 2] * t[2];
+    }
+}
+
+// ---- f1: one thread per candidate ----
+__global__ void __launch_bounds__(64)
+triangulate_kernel(TriArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    a.keep[i] = 1;
+    const int fp = a.first_pose[i];
+    if (a.n_poses > 1 && a.n_poses - fp <= a.min_frames) return;
+    if (fp < 0 || fp >= a.n_poses) { atomicOr(a.flags, 1); return; }
+    double past[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) past[k] = a.poses[12 * fp + k];
+    const double u = a.keys[2 * i], v = a.keys[2 * i + 1], u0 = a.first_keys[2 * i], v0 = a.first_keys[2 * i + 1];
+    {   // bearing angle between the two viewing rays (check_baseline)
+        const double ax = a.Ki[0] * u + a.Ki[2], ay = a.Ki[4] * v + a.Ki[5], az = 1.0;
+        double rel[9], M[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rel[3 * r + c] = past[r] * a.cur[c] + past[3 + r] * a.cur[3 + c] + past[6 + r] * a.cur[6 + c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) M[3 * r + c] = rel[3 * r] * a.Ki[c] + rel[3 * r + 1] * a.Ki[3 + c] + rel[3 * r + 2] * a.Ki[6 + c];
+        const double bx = M[0] * u0 + M[1] * v0 + M[2], by = M[3] * u0 + M[4] * v0 + M[5], bz = M[6] * u0 + M[7] * v0 + M[8];
+        double cs = (ax * bx + ay * by + az * bz) / (sqrt(ax * ax + ay * ay + az * az) * sqrt(bx * bx + by * by + bz * bz));
+        cs = cs < -1.0 ? -1.0 : (cs > 1.0 ? 1.0 : cs);
+        const double alpha = acos(cs) * (180.0 / 3.14159265358979323846);
+        if (alpha < a.min_angle_deg) return;
+    }
+    double Rc[9], tc[3], Pc[12], Rp[9], tp[3], Pp[12];
+    invert_pose(a.cur, Rc, tc);
+    proj_matrix(a.K, Rc, tc, Pc);
+    invert_pose(past, Rp, tp);
+    proj_matrix(a.K, Rp, tp, Pp);
+    double A[16], W[4], U[16], Vt[16], At[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        A[k] = u0 * Pp[8 + k] - Pp[k];
+        A[4 + k] = v0 * Pp[8 + k] - Pp[4 + k];
+        A[8 + k] = u * Pc[8 + k] - Pc[k];
+        A[12 + k] = v * Pc[8 + k] - Pc[4 + k];
+    }
+    jacobi_svd<4>(A, W, U, Vt, At);
+    const float X0 = (float)Vt[12], X1 = (float)Vt[13], X2 = (float)Vt[14], X3 = (float)Vt[15];
+    const float L0 = __fdiv_rn(X0, X3), L1 = __fdiv_rn(X1, X3), L2 = __fdiv_rn(X2, X3);
+    const double zc = Rc[6] * (double)L0 + Rc[7] * (double)L1 + Rc[8] * (double)L2 + tc[2];
+    const double zp = Rp[6] * (double)L0 + Rp[7] * (double)L1 + Rp[8] * (double)L2 + tp[2];
+    if (zc > a.min_dist && zp > a.min_dist && zc < a.max_dist && zp < a.max_dist) {
+        a.keep[i] = 0;
+        a.lm_slot[3 * i] = L0; a.lm_slot[3 * i + 1] = L1; a.lm_slot[3 * i + 2] = L2;
+    }
+}
+
+// ordered compaction of the accepted candidates (keep == 0): one CTA, ballot + running base
+__global__ void __launch_bounds__(1024)
+triangulate_compact_kernel(TriArgs a)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < a.n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool acc = i < a.n && a.keep[i] == 0;
+        const unsigned bm = __ballot_sync(0xffffffffu, acc);
+        if (lane == 0) s_warp[warp] = __popc(bm);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (acc) {
+            const int o = off + __popc(bm & ((1u << lane) - 1));
+            a.out_lm[3 * o] = a.lm_slot[3 * i]; a.out_lm[3 * o + 1] = a.lm_slot[3 * i + 1]; a.out_lm[3 * o + 2] = a.lm_slot[3 * i + 2];
+            a.out_kp[2 * o] = a.keys[2 * i]; a.out_kp[2 * o + 1] = a.keys[2 * i + 1];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 32; ++w) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *a.n_new = s_base;
+}
+
+extern "C" int b200vo_min_distance_mask(b200vo_ctx* ctx, const float* pts, int n, const float* existing, int m,
+                                        float min_dist, uint8_t* valid)
+{
+    if (!ctx || n < 0 || m < 0 || (n > 0 && (!pts || !valid)) || (m > 0 && !existing)) return B200VO_E_BADARG;
+    if (n == 0) return 0;
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const size_t b_p = vo_align((size_t)n * 8, 256), b_e = vo_align((size_t)(m > 0 ? m : 1) * 8, 256), b_v = vo_align((size_t)n, 256);
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[6], b_p + b_e + b_v));
+    VO_TRY(vo_reserve_pinned(ctx, b_p + b_e + b_v));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[6].p;
+    uint8_t* hp = (uint8_t*)ctx->h_pin;
+    memcpy(hp, pts, (size_t)n * 8);
+    if (m > 0) memcpy(hp + b_p, existing, (size_t)m * 8);
+    VO_CUDA(ctx, cudaMemcpyAsync(d, hp, b_p + b_e, cudaMemcpyHostToDevice, ctx->stream));
+    min_distance_kernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>((const float2*)d, n, (const float2*)(d + b_p), m, min_dist,
+                                                                      d + b_p + b_e);
+    ctx->launches++;
+    VO_CUDA(ctx, cudaGetLastError());
+    VO_CUDA(ctx, cudaMemcpyAsync(hp + b_p + b_e, d + b_p + b_e, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    memcpy(valid, hp + b_p + b_e, (size_t)n);
+    return 0;
+}
+
+extern "C" int b200vo_triangulate_landmarks(b200vo_ctx* ctx, const double K[9], double min_dist, double max_dist,
+                                            double min_baseline_angle_deg, int min_baseline_frames,
+                                            const float* first_keys, const float* keys, const int32_t* first_pose, int n,
+                                            const double* poses_cw, int n_poses, const double cur_pose_cw[12],
+                                            uint8_t* too_short_baseline, float* new_landmarks, float* new_keypoints,
+                                            int* n_new)
+{
+    if (!ctx || !K || !cur_pose_cw || !n_new || n < 0 || n_poses < 1 || !poses_cw) return B200VO_E_BADARG;
+    *n_new = 0;
+    if (n == 0) return 0;
+    if (!first_keys || !keys || !first_pose || !too_short_baseline || !new_landmarks || !new_keypoints)
+        return vo_set_err(ctx, B200VO_E_BADARG, "null pointer");
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    TriArgs a{};
+    for (int k = 0; k < 9; ++k) a.K[k] = K[k];
+    const double Ki[9] = {1.0 / K[0], 0, -K[2] / K[0], 0, 1.0 / K[4], -K[5] / K[4], 0, 0, 1};
+    for (int k = 0; k < 9; ++k) a.Ki[k] = Ki[k];
+    for (int k = 0; k < 12; ++k) a.cur[k] = cur_pose_cw[k];
+    a.min_dist = min_dist; a.max_dist = max_dist; a.min_angle_deg = min_baseline_angle_deg;
+    a.min_frames = min_baseline_frames; a.n = n; a.n_poses = n_poses;
+    // device layout: inputs [first_keys | keys | first_pose | poses] then outputs [keep | out_lm | out_kp | n_new,flags] + lm_slot
+    const size_t b_k = vo_align((size_t)n * 8, 256), b_fp = vo_align((size_t)n * 4, 256), b_ps = vo_align((size_t)n_poses * 96, 256);
+    const size_t b_keep = vo_align((size_t)n, 256), b_lm = vo_align((size_t)n * 12, 256), b_small = 256;
+    const size_t in_bytes = 2 * b_k + b_fp + b_ps, out_bytes = b_keep + b_lm + b_k + b_small;
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[7], in_bytes + out_bytes + b_lm));
+    VO_TRY(vo_reserve_pinned(ctx, in_bytes + out_bytes));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[7].p;
+    uint8_t* hp = (uint8_t*)ctx->h_pin;
+    memcpy(hp, first_keys, (size_t)n * 8);
+    memcpy(hp + b_k, keys, (size_t)n * 8);
+    memcpy(hp + 2 * b_k, first_pose, (size_t)n * 4);
+    memcpy(hp + 2 * b_k + b_fp, poses_cw, (size_t)n_poses * 96);
+    VO_CUDA(ctx, cudaMemcpyAsync(d, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    a.first_keys = (const float*)d; a.keys = (const float*)(d + b_k); a.first_pose = (const int*)(d + 2 * b_k);
+    a.poses = (const double*)(d + 2 * b_k + b_fp);
+    uint8_t* dout = d + in_bytes;
+    a.keep = dout; a.out_lm = (float*)(dout + b_keep); a.out_kp = (float*)(dout + b_keep + b_lm);
+    a.n_new = (int*)(dout + b_keep + b_lm + b_k); a.flags = a.n_new + 1;
+    a.lm_slot = (float*)(dout + out_bytes);
+    VO_CUDA(ctx, cudaMemsetAsync(a.n_new, 0, b_small, ctx->stream));
+    triangulate_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(a);
+    triangulate_compact_kernel<<<1, 1024, 0, ctx->stream>>>(a);
+    ctx->launches += 2;
+    VO_CUDA(ctx, cudaGetLastError());
+    uint8_t* ho = hp + in_bytes;
+    VO_CUDA(ctx, cudaMemcpyAsync(ho, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    const int* small = (const int*)(ho + b_keep + b_lm + b_k);
+    if (small[1] & 1) return vo_set_err(ctx, B200VO_E_BADARG, "first_pose index outside [0, n_poses)");
+    const int cnt = small[0];
+    memcpy(too_short_baseline, ho, (size_t)n);
+    memcpy(new_landmarks, ho + b_keep, (size_t)cnt * 12);
+    memcpy(new_keypoints, ho + b_keep + b_lm, (size_t)cnt * 8);
+    *n_new = cnt;
+    return 0;
+}

@@ -1,0 +1,76 @@
+"""Host side of the two components next to the hot path -- numpy in the reference,
+one or two kernel launches here.  Same argument meaning as the reference's own state arrays, so the
+binding is a two-line replacement:
+
+* ``min_distance_mask``      -> ``valid_dist`` of ``feature_adding``       (VisualOdometryPipeLine.py:258)
+* ``triangulate_landmarks``  -> the candidate loop of ``triangulate_landmarks`` (:170-204)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_f32p, c_f64p, c_i32p, c_u8p
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _chk(ctx, rc, what):
+    if rc == -2:   # B200VO_E_UNSUPPORTED
+        raise NotImplementedError(ctx.last_error())
+    if rc != 0:
+        raise _lib.B200VOError(f"{what} failed ({rc}): {ctx.last_error()}")
+
+
+def min_distance_mask(pts, potential_keys, min_dist, ctx: _lib.Context | None = None) -> np.ndarray:
+    """bool (n,): corner i is farther than ``min_dist`` from every existing candidate (ref :258)."""
+    ctx = ctx or _lib.default_context(0)
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    ex = np.ascontiguousarray(potential_keys, np.float32).reshape(-1, 2)
+    valid = np.zeros(len(pts), np.uint8)
+    if len(pts):
+        _chk(ctx, ctx.lib.b200vo_min_distance_mask(ctx.h, _p(pts, c_f32p), len(pts), _p(ex, c_f32p) if len(ex) else None, len(ex),
+                                                   C.c_float(min_dist), _p(valid, c_u8p)), "b200vo_min_distance_mask")
+    return valid.astype(bool)
+
+
+def pack_poses(transforms) -> np.ndarray:
+    """``self.transforms`` ([(R_CW (3,3), t_CW (3,1)), ...]) -> float64 (n,12) rows (R row-major | t)."""
+    return np.ascontiguousarray([np.hstack([np.reshape(R, 9), np.reshape(t, 3)]) for R, t in transforms], np.float64).reshape(-1, 12)
+
+
+def triangulate_landmarks(K, options, potential_first_keys, potential_keys, potential_transforms, transforms,
+                          R_current_CW, t_current_CW, ctx: _lib.Context | None = None):
+    """The candidate loop of the reference's ``triangulate_landmarks`` (:170-204).
+
+    ``options`` needs ``min_dist_landmarks, max_dist_landmarks, min_baseline_angle, min_baseline_frames``
+    (main.py:21-25); ``transforms`` is ``self.transforms`` (a list of (R_CW, t_CW)) or a packed (n,12) array.
+    Returns ``(too_short_baseline bool (n,), new_landmarks float32 (k,3), new_keypoints float32 (k,2))``:
+    the mask the reference passes to ``filter_potential`` (:206) and the rows it appends to
+    ``matched_landmarks`` / ``matched_keypoints`` (:196-202)."""
+    ctx = ctx or _lib.default_context(0)
+    fk = np.ascontiguousarray(potential_first_keys, np.float32).reshape(-1, 2)
+    k = np.ascontiguousarray(potential_keys, np.float32).reshape(-1, 2)
+    fp = np.ascontiguousarray(np.asarray(potential_transforms).reshape(-1), np.int32)
+    poses = transforms if isinstance(transforms, np.ndarray) else pack_poses(transforms)
+    poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 12)
+    cur = np.ascontiguousarray(np.hstack([np.reshape(R_current_CW, 9), np.reshape(t_current_CW, 3)]), np.float64)
+    Kf = np.ascontiguousarray(K, np.float64).reshape(9)
+    n = len(k)
+    if len(fk) != n or len(fp) != n:
+        raise ValueError("potential_first_keys, potential_keys and potential_transforms must have one row per candidate")
+    keep = np.zeros(n, np.uint8)
+    lm = np.zeros((max(n, 1), 3), np.float32)
+    kp = np.zeros((max(n, 1), 2), np.float32)
+    cnt = C.c_int(0)
+    if n:
+        _chk(ctx, ctx.lib.b200vo_triangulate_landmarks(
+            ctx.h, _p(Kf, c_f64p), C.c_double(options['min_dist_landmarks']), C.c_double(options['max_dist_landmarks']),
+            C.c_double(options['min_baseline_angle']), int(options['min_baseline_frames']), _p(fk, c_f32p), _p(k, c_f32p),
+            _p(fp, c_i32p), n, _p(poses, c_f64p), len(poses), _p(cur, c_f64p), _p(keep, c_u8p), _p(lm, c_f32p), _p(kp, c_f32p),
+            C.byref(cnt)), "b200vo_triangulate_landmarks")
+    return keep.astype(bool), lm[:cnt.value].copy(), kp[:cnt.value].copy()

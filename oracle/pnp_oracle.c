@@ -62,7 +62,7 @@ static double quad3(const double* M, const double* u, const double* v)
  * control points c_k = c_0 + sqrt(d_k/n) u_k depend on the sign of u_k, and under noise the
  * EPnP pose depends on the control points at the 1e-4 level.  Checked against
  * cv2.SVDecomp in tests/test_oracle_pnp.py. */
-static void jacobi_svd(const double* A, int m, int n, double* W, double* U, double* Vt)
+void orc_jacobi_svd(const double* A, int m, int n, double* W, double* U, double* Vt)
 {
     double At[12 * 12], Wd[12];
     const double eps = DBL_EPSILON * 10;
@@ -450,14 +450,14 @@ void orc_pnp_errors(const float* obj, const float* img, int n, const double K[9]
 static void svd3_sym_desc(const double* S, double* d, double* Ut)
 {   /* cvSVD(S, D, Ut, 0, CV_SVD_U_T): rows of Ut = left singular vectors */
     double U[9], Vt[9];
-    jacobi_svd(S, 3, 3, d, U, Vt);
+    orc_jacobi_svd(S, 3, 3, d, U, Vt);
     for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) Ut[3 * i + k] = U[3 * k + i];
 }
 
 static void svd3(const double* A, double* U, double* s, double* V)
 {   /* A = U diag(s) V^T */
     double Vt[9];
-    jacobi_svd(A, 3, 3, s, U, Vt);
+    orc_jacobi_svd(A, 3, 3, s, U, Vt);
     for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) V[3 * i + k] = Vt[3 * k + i];
 }
 
@@ -584,7 +584,7 @@ int orc_epnp(const double* obj, const double* img, int n, const double K[9], dou
             for (int c = 0; c < 12; ++c) MtM[12 * r + c] += m1[r] * m1[c] + m2[r] * m2[c];
     }
     double w[12], Um[144], Vtm[144], ut[144];
-    jacobi_svd(MtM, 12, 12, w, Um, Vtm);
+    orc_jacobi_svd(MtM, 12, 12, w, Um, Vtm);
     for (int i = 0; i < 12; ++i)
         for (int k = 0; k < 12; ++k) ut[12 * i + k] = Um[12 * k + i];   /* rows: descending singular value */
     /* L (6x10) and rho */

@@ -74,6 +74,22 @@ int orc_find_essential_mat_ransac(const float* p1, const float* p2, int n, const
                                   double prob, double thr, int max_iters, double E[9],
                                   uint8_t* mask, int* found, int* iters_run);
 
+/* OpenCV's small-matrix SVD (one-sided Jacobi, lapack.cpp JacobiSVDImpl_), m >= n <= 12, row-major */
+void orc_jacobi_svd(const double* A, int m, int n, double* W, double* U, double* Vt);
+
+/* ---- "next" rows, SURVEY 8f (the reference does these in numpy + cv2.triangulatePoints) ---- */
+/* f2, ref :258: valid[i] = all_j ( sqrtf(fl(dx^2) + fl(dy^2)) > min_dist ) in float32 */
+void orc_min_distance_mask(const float* pts, int n, const float* existing, int m, float min_dist, uint8_t* valid);
+/* f1, ref :107-206 triangulate_landmarks: age gate, bearing-angle gate, cv2.triangulatePoints (4x4 DLT,
+ * Jacobi SVD, float32 homogeneous output), depth window in both views.  poses are (R_CW row-major | t_CW)
+ * as the reference stores them in self.transforms.  keep[i] = too_short_baseline[i]; accepted landmarks
+ * and their keypoints are appended in candidate order. */
+int orc_triangulate_landmarks(const double K[9], double min_dist, double max_dist, double min_angle_deg,
+                              int min_frames, const float* first_keys, const float* keys,
+                              const int32_t* first_pose, int n, const double* poses_cw, int n_poses,
+                              const double cur_cw[12], uint8_t* keep, float* new_landmarks,
+                              float* new_keypoints, int* n_new);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,10 @@ Imports VisualOdometryPipeLine from /root/reference (read-only, never copied), r
 monocular_visual_odometry_va4mr_b200/synth.py; the datasets of utils.py are not available offline)
 with the real cv2, and wraps the five cv2 names the class calls on the hot path
 (VisualOdometryPipeLine.py:229, :256, :281, :287, :308, :343) so that every call's inputs and cv2's
-outputs are written to tests/golden/reference_trace.npz.  The parity tests replay each call
+outputs are written to tests/golden/reference_trace.npz.  The two numpy components next to the hot
+path are recorded at method level: `triangulate_landmarks` (:107-206; inputs = the
+candidate state + poses, outputs = the mask handed to filter_potential and the appended rows) and
+`feature_adding` (:248-268; the min-distance mask of :258).  The parity tests replay each call
 ("teacher-forced") through the oracle (CPU) and through the C-ABI (GPU).
 
 Frames are NOT stored: the fixture keeps the render parameters and a CRC32 per frame; the tests
@@ -54,7 +57,7 @@ def main():
                frame_crc=np.array([zlib.crc32(f.tobytes()) for f in frame_list], np.uint32),
                K=s["K"], cv2_version=np.array(cv2.__version__))
     calls = []   # (kind, index within kind)
-    n = dict(klt=0, gftt=0, knn=0, emat=0, pnp=0)
+    n = dict(klt=0, gftt=0, knn=0, emat=0, pnp=0, tri=0, fadd=0)
     real = dict(klt=cv2.calcOpticalFlowPyrLK, gftt=cv2.goodFeaturesToTrack, bf=cv2.BFMatcher,
                 emat=cv2.findEssentialMat, pnp=cv2.solvePnPRansac)
 
@@ -112,6 +115,60 @@ def main():
         calls.append(("pnp", i))
         return out
 
+    # ---- the two "next" rows of SURVEY.md 8f, recorded at method level (they are numpy, not cv2 calls) ----
+    orig_tri = VisualOdometryPipeLine.triangulate_landmarks
+    orig_add = VisualOdometryPipeLine.feature_adding
+
+    def tri(self, R_cur, t_cur):
+        i = n["tri"]; n["tri"] += 1
+        nk = len(self.potential_keys)
+        rec[f"tri{i}_first_keys"] = np.array(self.potential_first_keys, copy=True)
+        rec[f"tri{i}_keys"] = np.array(self.potential_keys, copy=True)
+        rec[f"tri{i}_first_pose"] = np.array(self.potential_transforms, copy=True).reshape(-1).astype(np.int32)
+        rec[f"tri{i}_poses"] = np.array([np.hstack([R.reshape(9), np.reshape(t, 3)]) for R, t in self.transforms], np.float64)
+        rec[f"tri{i}_cur"] = np.hstack([np.reshape(R_cur, 9), np.reshape(t_cur, 3)]).astype(np.float64)
+        n_lm0 = len(self.matched_landmarks)
+        grabbed = {}
+        orig_filter = self.filter_potential
+
+        def grab(mask):
+            grabbed["mask"] = np.array(mask, copy=True)
+            return orig_filter(mask)
+
+        self.filter_potential = grab
+        try:
+            out = orig_tri(self, R_cur, t_cur)
+        finally:
+            del self.filter_potential
+        assert len(grabbed["mask"]) == nk
+        rec[f"tri{i}_keep"] = grabbed["mask"].astype(np.uint8)
+        rec[f"tri{i}_landmarks"] = np.array(self.matched_landmarks[n_lm0:], copy=True)
+        rec[f"tri{i}_keypoints"] = np.array(self.matched_keypoints[n_lm0:], copy=True)
+        rec[f"tri{i}_lm_dtype"] = np.array(str(np.asarray(self.matched_landmarks).dtype))
+        calls.append(("tri", i))
+        return out
+
+    def fadd(self, img):
+        i = n["fadd"]; n["fadd"] += 1
+        existing = np.array(self.potential_keys, copy=True)
+        n_gftt = n["gftt"]
+        out = orig_add(self, img)
+        pts = rec[f"gftt{n_gftt}_out"].squeeze()
+        # the reference's own expression (:258), evaluated on the recorded inputs
+        valid = np.array([np.all(np.linalg.norm(pts[j, :] - existing, axis=1) > OPTIONS['feature_min_dist']) for j in range(pts.shape[0])])
+        assert np.array_equal(np.asarray(self.potential_keys)[len(existing):], pts[valid])
+        rec[f"fadd{i}_existing"] = existing
+        rec[f"fadd{i}_gftt"] = np.array(n_gftt)
+        rec[f"fadd{i}_valid"] = valid.astype(np.uint8)
+        rec[f"fadd{i}_min_dist"] = np.array(float(OPTIONS['feature_min_dist']))
+        calls.append(("fadd", i))
+        return out
+
+    VisualOdometryPipeLine.triangulate_landmarks = tri
+    VisualOdometryPipeLine.feature_adding = fadd
+    rec["tri_cfg"] = np.array([OPTIONS['min_dist_landmarks'], OPTIONS['max_dist_landmarks'], OPTIONS['min_baseline_angle'],
+                               OPTIONS['min_baseline_frames']], np.float64)
+
     cv2.calcOpticalFlowPyrLK, cv2.goodFeaturesToTrack, cv2.BFMatcher = klt, gftt, Matcher
     cv2.findEssentialMat, cv2.solvePnPRansac = emat, pnp
     try:
@@ -123,6 +180,7 @@ def main():
     finally:
         cv2.calcOpticalFlowPyrLK, cv2.goodFeaturesToTrack, cv2.BFMatcher = real["klt"], real["gftt"], real["bf"]
         cv2.findEssentialMat, cv2.solvePnPRansac = real["emat"], real["pnp"]
+        VisualOdometryPipeLine.triangulate_landmarks, VisualOdometryPipeLine.feature_adding = orig_tri, orig_add
     rec["calls"] = np.array([f"{k}{i}" for k, i in calls])
     rec["num_pts"] = np.array(vo.num_pts)
     np.savez_compressed(OUT, **rec)

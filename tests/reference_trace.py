@@ -65,9 +65,25 @@ def check_pnp(g, i, run):
         assert np.abs(np.ravel(tv) - g[f"pnp{i}_tvec"].ravel()).max() < 1e-6 * max(1.0, np.abs(g[f"pnp{i}_tvec"]).max())
 
 
+def check_tri(g, i, run):
+    keep, lm, kp = run(g["K"], g["tri_cfg"], g[f"tri{i}_first_keys"], g[f"tri{i}_keys"], g[f"tri{i}_first_pose"],
+                       g[f"tri{i}_poses"], g[f"tri{i}_cur"])
+    assert np.array_equal(keep, g[f"tri{i}_keep"].astype(bool)), f"tri{i}: too_short_baseline"
+    ref = g[f"tri{i}_landmarks"].reshape(-1, 3)
+    assert lm.shape == ref.shape and np.array_equal(kp, g[f"tri{i}_keypoints"].reshape(-1, 2))
+    if len(ref):
+        assert np.all(np.abs(lm - ref) <= np.spacing(np.abs(ref))), f"tri{i}: landmarks"     # <= 1 float32 ulp
+
+
+def check_fadd(g, i, run):
+    pts = g[f"gftt{int(g[f'fadd{i}_gftt'])}_out"].reshape(-1, 2)
+    valid = run(pts, g[f"fadd{i}_existing"], float(g[f"fadd{i}_min_dist"]))
+    assert np.array_equal(valid, g[f"fadd{i}_valid"].astype(bool)), f"fadd{i}"
+
+
 def replay(impl):
     g, frames = load()
-    seen = dict(klt=0, gftt=0, knn=0, emat=0, pnp=0)
+    seen = dict(klt=0, gftt=0, knn=0, emat=0, pnp=0, tri=0, fadd=0)
     for name in g["calls"]:
         name = str(name)
         kind, i = name.rstrip("0123456789"), int(name[len(name.rstrip("0123456789")):])
@@ -82,5 +98,10 @@ def replay(impl):
             check_emat(g, i, impl.emat)
         elif kind == "pnp":
             check_pnp(g, i, impl.pnp)
+        elif kind == "tri":
+            check_tri(g, i, impl.tri)
+        elif kind == "fadd":
+            check_fadd(g, i, impl.fadd)
     assert seen["klt"] >= 2 and seen["gftt"] >= 1 and seen["knn"] == 1 and seen["emat"] == 1 and seen["pnp"] >= 1
+    assert seen["tri"] >= 2 and seen["fadd"] >= 1
     return seen

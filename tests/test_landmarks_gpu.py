@@ -1,0 +1,70 @@
+"""CUDA versions of the two components next to the hot path through the C ABI: identical
+masks and appended rows as the unmodified reference class produced (tests/golden/reference_trace.npz),
+as the oracle, and as the reference's own numpy expression / live cv2.triangulatePoints."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from monocular_visual_odometry_va4mr_b200 import hotpath
+
+pytestmark = pytest.mark.gpu
+OPT = lambda cfg: dict(min_dist_landmarks=cfg[0], max_dist_landmarks=cfg[1], min_baseline_angle=cfg[2], min_baseline_frames=int(cfg[3]))
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN, "reference_trace.npz"))
+
+
+def test_min_distance_mask_vs_reference_trace_and_oracle(g):
+    import oracle
+    n = sum(1 for k in g.files if k.startswith("fadd") and k.endswith("_valid"))
+    for i in range(n):
+        pts = g[f"gftt{int(g[f'fadd{i}_gftt'])}_out"].reshape(-1, 2)
+        valid = hotpath.min_distance_mask(pts, g[f"fadd{i}_existing"], float(g[f"fadd{i}_min_dist"]))
+        assert valid.dtype == bool and np.array_equal(valid, g[f"fadd{i}_valid"].astype(bool)), i
+    rng = np.random.default_rng(5)
+    for n, m in ((1400, 3000), (300, 700), (1, 1), (50, 0), (0, 40), (33, 31)):
+        pts = np.rint(rng.uniform(0, 1200, (n, 2))).astype(np.float32)
+        ex = rng.uniform(0, 1200, (m, 2)).astype(np.float32)
+        if n > 1 and m > 1:   # exact ties: distance == 10 is NOT > 10; one float32 step above is
+            ex[0] = pts[0] + np.float32([6, 8])
+            ex[1] = pts[1] + np.float32([6, np.nextafter(np.float32(8), np.float32(9))])
+        ref = np.array([np.all(np.linalg.norm(pts[i, :] - ex, axis=1) > 10) for i in range(n)], bool)        # ref :258
+        got = hotpath.min_distance_mask(pts, ex, 10.0)
+        assert np.array_equal(got, ref) and np.array_equal(got, oracle.min_distance_mask(pts, ex, 10.0)), (n, m)
+
+
+def test_triangulate_vs_reference_trace_and_oracle(g):
+    import oracle
+    n = sum(1 for k in g.files if k.startswith("tri") and k.endswith("_keep"))
+    assert n >= 4
+    for i in range(n):
+        args = (g[f"tri{i}_first_keys"], g[f"tri{i}_keys"], g[f"tri{i}_first_pose"], g[f"tri{i}_poses"])
+        keep, lm, kp = hotpath.triangulate_landmarks(g["K"], OPT(g["tri_cfg"]), *args, g[f"tri{i}_cur"][:9].reshape(3, 3), g[f"tri{i}_cur"][9:])
+        assert np.array_equal(keep, g[f"tri{i}_keep"].astype(bool)), f"tri{i}: too_short_baseline"
+        ref = g[f"tri{i}_landmarks"].reshape(-1, 3)
+        assert lm.shape == ref.shape and lm.dtype == np.float32
+        assert np.array_equal(kp, g[f"tri{i}_keypoints"].reshape(-1, 2))
+        if len(ref):
+            assert np.all(np.abs(lm - ref) <= np.spacing(np.abs(ref))), f"tri{i}: landmarks vs the reference's"      # <= 1 float32 ulp
+        ko, lo, po = oracle.triangulate_landmarks(g["K"], g["tri_cfg"], *args, g[f"tri{i}_cur"])
+        assert np.array_equal(keep, ko) and np.array_equal(kp, po)
+        assert np.array_equal(lm, lo), f"tri{i}: landmarks vs the oracle (same arithmetic: bit-equal)"
+
+
+def test_triangulate_edges():
+    K = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1]])
+    opt = dict(min_dist_landmarks=1, max_dist_landmarks=150, min_baseline_angle=2, min_baseline_frames=2)
+    keep, lm, kp = hotpath.triangulate_landmarks(K, opt, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), np.zeros((0, 1)),
+                                                 [(np.eye(3), np.zeros((3, 1)))], np.eye(3), np.zeros((3, 1)))
+    assert keep.shape == (0,) and lm.shape == (0, 3) and kp.shape == (0, 2)
+    # identical poses: zero parallax -> every candidate stays (too short baseline), nothing is appended
+    pts = np.float32([[100, 100], [640, 180], [900, 300]])
+    keep, lm, kp = hotpath.triangulate_landmarks(K, opt, pts, pts, np.zeros(3), [(np.eye(3), np.zeros((3, 1)))], np.eye(3), np.zeros((3, 1)))
+    assert keep.all() and len(lm) == 0
+    with pytest.raises(Exception):
+        hotpath.triangulate_landmarks(K, dict(opt, min_baseline_frames=-5), pts, pts, np.full(3, 7), [(np.eye(3), np.zeros((3, 1)))],
+                                      np.eye(3), np.zeros((3, 1)))

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import reference_trace
-from monocular_visual_odometry_va4mr_b200 import cv2_compat
+from monocular_visual_odometry_va4mr_b200 import cv2_compat, hotpath
 
 pytestmark = pytest.mark.gpu
 
@@ -36,6 +36,12 @@ def _pnp(obj, img, K, iters, err, conf):
                                      reprojectionError=err, iterationsCount=iters)                              # :343
 
 
+def _tri(K, cfg, first_keys, keys, first_pose, poses, cur):                                                      # :170-204
+    opt = dict(min_dist_landmarks=cfg[0], max_dist_landmarks=cfg[1], min_baseline_angle=cfg[2], min_baseline_frames=int(cfg[3]))
+    return hotpath.triangulate_landmarks(K, opt, first_keys, keys, first_pose, poses, cur[:9].reshape(3, 3), cur[9:])
+
+
 def test_cuda_replays_reference_trace():
-    seen = reference_trace.replay(SimpleNamespace(klt=_klt, gftt=_gftt, knn=_knn, emat=_emat, pnp=_pnp))
+    seen = reference_trace.replay(SimpleNamespace(klt=_klt, gftt=_gftt, knn=_knn, emat=_emat, pnp=_pnp, tri=_tri,
+                                                  fadd=hotpath.min_distance_mask))                             # :258
     assert sum(seen.values()) >= 10
