@@ -7,7 +7,7 @@
 // double), because the ordered corner list is decided by last-bit ties between symmetric
 // corners.  Pipeline:
 //   gftt_cov_kernel        Sobel (scaled) -> Dx^2, DxDy, Dy^2             (1 thread / pixel)
-//   gftt_box_eig_kernel    3x3 box as running column sums in double, eig  (1 thread / column)
+//   gftt_rowsum/colsum/eig 3x3 box as running column sums in double (serial chain per column and plane), eig
 //   gftt_candidates_kernel threshold at q*max, 3x3 non-maximum test, compaction of 64-bit keys
 //   gftt_rank_kernel       order by (value desc, address desc): rank by counting (n <= 32768)
 //   gftt_bitonic_*         same order for larger candidate sets
@@ -52,48 +52,75 @@ gftt_cov_kernel(const uint8_t* __restrict__ img, int pitch, int w, int h, float 
     c[0] = __fmul_rn(dx, dx); c[1] = __fmul_rn(dx, dy); c[2] = __fmul_rn(dy, dy);
 }
 
-// one thread per column: running column sum (double) of the double row sums, then the eigenvalue
-__global__ void __launch_bounds__(128)
-gftt_box_eig_kernel(const float* __restrict__ cov, int w, int h, float* __restrict__ eig, int* __restrict__ max_bits)
+// 3x3 box filter of the three covariance planes exactly as cv2's boxFilter<float -> double -> float>
+// runs it: row sums in double, then a RUNNING column sum in double (SUM += entering row, emit,
+// SUM -= leaving row) whose rounding history is part of the result -- so the sum down a column is a
+// serial chain.  Split in three so that only the chain itself is serial:
+//   gftt_rowsum_kernel   rs[yy+1][ch][x] = double row sum of row yy (REFLECT_101), yy = -1 .. h  (parallel)
+//   gftt_colsum_kernel   one thread per (column, plane): the chain, prefetching 8 rows ahead
+//   gftt_eig_kernel      a + c - sqrt((a - c)^2 + b^2) and the global maximum                   (parallel)
+__global__ void __launch_bounds__(256)
+gftt_rowsum_kernel(const float* __restrict__ cov, int w, int h, double* __restrict__ rs)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    float vmax = 0.f;
-    if (x < w) {
-        const int xm = refl101(x - 1, w), xp = refl101(x + 1, w);
-        auto rowsum = [&](int yy, double* o) {
-            const float* r = cov + 3 * (size_t)refl101(yy, h) * w;
+    const int yy = (int)blockIdx.y - 1;
+    if (x >= w) return;
+    const int xm = refl101(x - 1, w), xp = refl101(x + 1, w);
+    const float* r = cov + 3 * (size_t)refl101(yy, h) * w;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch)
-                o[ch] = __dadd_rn(__dadd_rn((double)r[3 * xm + ch], (double)r[3 * x + ch]), (double)r[3 * xp + ch]);
-        };
-        double SUM[3] = {0., 0., 0.}, prev1[3], prev0[3], cur[3];
-        rowsum(-1, prev1);   // leaving row for y = 0
-        rowsum(0, prev0);
+    for (int ch = 0; ch < 3; ++ch)
+        rs[((size_t)(yy + 1) * 3 + ch) * w + x] = __dadd_rn(__dadd_rn((double)r[3 * xm + ch], (double)r[3 * x + ch]), (double)r[3 * xp + ch]);
+}
+
+__global__ void __launch_bounds__(32)
+gftt_colsum_kernel(const double* __restrict__ rs, int w, int h, float* __restrict__ box /* [3][h][w] */)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * w) return;
+    const int ch = t / w, x = t - ch * w;
+    const double* col = rs + (size_t)ch * w + x;           // row yy at col[(yy + 1) * 3 * w]
+    const size_t rstep = (size_t)3 * w;
+    float* out = box + (size_t)ch * w * h + x;
+    double prev1 = col[0], prev0 = col[rstep];
+    double SUM = __dadd_rn(__dadd_rn(0., prev1), prev0);
+    constexpr int RB = 8;
+    double nxt[RB];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) SUM[ch] = __dadd_rn(__dadd_rn(0., prev1[ch]), prev0[ch]);
-        for (int y = 0; y < h; ++y) {
-            rowsum(y + 1, cur);
-            float bx[3];
+    for (int k = 0; k < RB; ++k) nxt[k] = (k + 1 <= h) ? col[(size_t)(k + 2) * rstep] : 0.;
+    for (int y0 = 0; y0 < h; y0 += RB) {
+        double blk[RB];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const double s0 = __dadd_rn(SUM[ch], cur[ch]);
-                bx[ch] = (float)s0;
-                SUM[ch] = __dsub_rn(s0, prev1[ch]);
-                prev1[ch] = prev0[ch]; prev0[ch] = cur[ch];
+        for (int k = 0; k < RB; ++k) blk[k] = nxt[k];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) nxt[k] = (y0 + RB + k + 1 <= h) ? col[(size_t)(y0 + RB + k + 2) * rstep] : 0.;
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const int y = y0 + k;
+            if (y < h) {
+                const double s0 = __dadd_rn(SUM, blk[k]);
+                out[(size_t)y * w] = (float)s0;
+                SUM = __dsub_rn(s0, prev1);
+                prev1 = prev0; prev0 = blk[k];
             }
-            const float a = __fmul_rn(bx[0], 0.5f), b = bx[1], c = __fmul_rn(bx[2], 0.5f);
-            const float t = __fsub_rn(a, c);
-            const float v = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
-            eig[(size_t)y * w + x] = v;
-            vmax = fmaxf(vmax, v);
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+gftt_eig_kernel(const float* __restrict__ box, int w, int h, float* __restrict__ eig, int* __restrict__ max_bits)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, npx = (size_t)w * h;
+    float v = 0.f;
+    if (i < npx) {
+        const float a = __fmul_rn(box[i], 0.5f), b = box[npx + i], c = __fmul_rn(box[2 * npx + i], 0.5f);
+        const float t = __fsub_rn(a, c);
+        v = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+        eig[i] = v;
+    }
     // eig >= 0 up to rounding; negative values never win the max (cv2's max would be >= 0 too)
-    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 16));
-    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 8));
-    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 4));
-    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 2));
-    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
+    float vmax = fmaxf(v, 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     if ((threadIdx.x & 31) == 0) atomicMax(max_bits, __float_as_int(vmax));
 }
 
@@ -232,6 +259,89 @@ gftt_select_kernel(const unsigned long long* __restrict__ sorted, const int* __r
     if (lane == 0) *n_out = n_acc;
 }
 
+// Same greedy selection with the cell grid in shared memory (16 B per cell: up to four accepted
+// corners as x | y << 16, ~0 = empty -- corners of one cell are pairwise >= min_dist apart, a
+// cell is round(min_dist) wide, so at most two or three ever share one).  256 threads clear the
+// grid, one warp runs the selection; every neighbourhood test is nine independent LDS.128.
+#define GFTT_SCELL_CAP 4
+__global__ void __launch_bounds__(256)
+gftt_select_smem_kernel(const unsigned long long* __restrict__ sorted, const int* __restrict__ n_keys, int cap, int w, int h,
+                        int max_corners, double min_dist, int cell, int gw, int gh, float* __restrict__ corners,
+                        int* __restrict__ n_out)
+{
+    extern __shared__ uint4 s_cells[];
+    for (int i = threadIdx.x; i < gw * gh; i += blockDim.x) s_cells[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int n = min(*n_keys, cap);
+    const double md2 = min_dist * min_dist;
+    int n_acc = 0;
+    const int limit = max_corners > 0 ? max_corners : 0x7fffffff;
+    unsigned long long key_next = lane < n ? sorted[lane] : 0ull;
+    for (int i0 = 0; i0 < n && n_acc < limit; i0 += 32) {
+        const int i = i0 + lane;
+        int x = 0, y = 0;
+        bool alive = i < n;
+        const unsigned long long key = key_next;
+        if (i + 32 < n) key_next = sorted[i + 32];      // the next chunk's keys travel while this chunk is resolved
+        if (alive) {
+            const int idx = (int)(key & 0xffffffffu);
+            y = idx / w; x = idx - y * w;
+            const int xc = x / cell, yc = y / cell;
+#pragma unroll
+            for (int dyc = -1; dyc <= 1; ++dyc)
+#pragma unroll
+                for (int dxc = -1; dxc <= 1; ++dxc) {
+                    const int xx = xc + dxc, yy = yc + dyc;
+                    if (xx < 0 || yy < 0 || xx >= gw || yy >= gh) continue;
+                    const uint4 c = s_cells[yy * gw + xx];
+                    const unsigned pv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int j = 0; j < GFTT_SCELL_CAP; ++j) {
+                        if (pv[j] == ~0u) continue;
+                        const float dx = (float)(x - (int)(pv[j] & 0xffff)), dy = (float)(y - (int)(pv[j] >> 16));
+                        if ((double)(dx * dx + dy * dy) < md2) alive = false;
+                    }
+                }
+        }
+        // survivors of this chunk, in priority order: a survivor is accepted iff no ACCEPTED earlier
+        // survivor of the chunk lies within min_dist.  Every lane first collects the bit mask of earlier
+        // survivors in conflict with it (32 independent shuffles), then the acceptance recurrence runs
+        // on bit masks, identically in every lane (one shuffle per survivor instead of a ballot loop).
+        const unsigned surv = __ballot_sync(0xffffffffu, alive);
+        unsigned accepted = 0;
+        if (surv) {
+            unsigned conf = 0;
+#pragma unroll
+            for (int f = 0; f < 32; ++f) {          // 64 independent shuffles, fully pipelined
+                const int fx = __shfl_sync(0xffffffffu, x, f), fy = __shfl_sync(0xffffffffu, y, f);
+                const float dx = (float)(x - fx), dy = (float)(y - fy);
+                if (f < lane && ((surv >> f) & 1u) && (double)(dx * dx + dy * dy) < md2) conf |= 1u << f;
+            }
+            unsigned cf[32];
+#pragma unroll
+            for (int f = 0; f < 32; ++f) cf[f] = __shfl_sync(0xffffffffu, conf, f);
+            int room = limit - n_acc;
+#pragma unroll
+            for (int f = 0; f < 32; ++f)
+                if (((surv >> f) & 1u) && !(cf[f] & accepted) && room > 0) { accepted |= 1u << f; --room; }
+        }
+        if ((accepted >> lane) & 1u) {
+            const int o = n_acc + __popc(accepted & ((1u << lane) - 1));
+            corners[2 * o] = (float)x; corners[2 * o + 1] = (float)y;
+            unsigned* cp = reinterpret_cast<unsigned*>(&s_cells[(y / cell) * gw + (x / cell)]);
+            const unsigned val = (unsigned)x | ((unsigned)y << 16);
+#pragma unroll
+            for (int j = 0; j < GFTT_SCELL_CAP; ++j)
+                if (atomicCAS(cp + j, ~0u, val) == ~0u) break;
+        }
+        n_acc += __popc(accepted);
+        __syncwarp();
+    }
+    if (lane == 0) *n_out = n_acc;
+}
+
 extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img, int rows, int cols, size_t step,
                                              int max_corners, double quality, double min_dist, int block_size,
                                              float* corners_xy, int* n_out)
@@ -270,8 +380,11 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
     const size_t b_cnt = vo_align((size_t)gw * gh * 4, 256), b_pts = vo_align((size_t)gw * gh * GFTT_CELL_CAP * 4, 256);
     const size_t out_cap = max_corners > 0 ? (size_t)max_corners : npx;
     const size_t b_out = vo_align(out_cap * 8, 256), b_small = 256;
-    VO_TRY(vo_reserve(ctx, ctx->d_scratch[2], b_cov + b_eig + 2 * b_keys + b_cnt + b_pts + b_out + b_small));
+    const size_t b_rs = vo_align((size_t)(h + 2) * 3 * w * 8, 256), b_box = vo_align(npx * 12, 256);
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[2], b_cov + b_eig + 2 * b_keys + b_cnt + b_pts + b_out + b_small + b_rs + b_box));
     uint8_t* d = (uint8_t*)ctx->d_scratch[2].p;
+    double* d_rs = (double*)(d + b_cov + b_eig + 2 * b_keys + b_cnt + b_pts + b_out + b_small);
+    float* d_box = (float*)((uint8_t*)d_rs + b_rs);
     float* d_cov = (float*)d; d += b_cov;
     float* d_eig = (float*)d; d += b_eig;
     unsigned long long* d_keys = (unsigned long long*)d; d += b_keys;
@@ -286,7 +399,10 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
     {
         dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
         gftt_cov_kernel<<<grd, blk, 0, ctx->stream>>>(d_img, g.pitch[0], w, h, (float)scale, (float)(2.0 * scale), d_cov);
-        gftt_box_eig_kernel<<<(w + 127) / 128, 128, 0, ctx->stream>>>(d_cov, w, h, d_eig, d_small);
+        gftt_rowsum_kernel<<<dim3((w + 255) / 256, h + 2), 256, 0, ctx->stream>>>(d_cov, w, h, d_rs);
+        gftt_colsum_kernel<<<(3 * w + 31) / 32, 32, 0, ctx->stream>>>(d_rs, w, h, d_box);
+        gftt_eig_kernel<<<(int)((npx + 255) / 256), 256, 0, ctx->stream>>>(d_box, w, h, d_eig, d_small);
+        ctx->launches += 2;
         dim3 grd2((w - 2 + 31) / 32, (h - 2 + 7) / 8);
         gftt_candidates_kernel<<<grd2, blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys, d_small + 1, cap);
         ctx->launches += 3;
@@ -312,8 +428,16 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
             }
         d_order = d_keys;
     }
-    gftt_select_kernel<<<1, 32, 0, ctx->stream>>>(d_order, d_small + 1, cap, w, h, max_corners, min_dist, cell, gw, gh, d_cnt,
-                                                  d_pts, d_out, d_small + 2);
+    const size_t cell_smem = (size_t)gw * gh * sizeof(uint4);
+    if (min_dist >= 1 && cell_smem <= 200 * 1024) {
+        if (cell_smem > 48 * 1024)
+            VO_CUDA(ctx, cudaFuncSetAttribute(gftt_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
+        gftt_select_smem_kernel<<<1, 256, cell_smem, ctx->stream>>>(d_order, d_small + 1, cap, w, h, max_corners, min_dist, cell, gw,
+                                                                    gh, d_out, d_small + 2);
+    } else {
+        gftt_select_kernel<<<1, 32, 0, ctx->stream>>>(d_order, d_small + 1, cap, w, h, max_corners, min_dist, cell, gw, gh, d_cnt,
+                                                      d_pts, d_out, d_small + 2);
+    }
     ctx->launches++;
     VO_CUDA(ctx, cudaGetLastError());
     VO_CUDA(ctx, cudaMemcpyAsync(h_small, d_small, 16, cudaMemcpyDeviceToHost, ctx->stream));
