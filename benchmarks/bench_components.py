@@ -99,6 +99,12 @@ def main():
             if cv2 is not None:
                 r["cv2_ms"] = med(lambda: cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.99, threshold=1), 5, 1)
             print(json.dumps(r))
+            E, _ = cv2_compat.findEssentialMat(p1, p2, K, method=cv2_compat.RANSAC, prob=0.99, threshold=1)
+            wall = med(lambda: cv2_compat.recoverPose(E, p1, p2, K), args.reps)
+            r = {"workload": f"recoverPose N={n} (ref :315)", "wall_ms": wall, "gpu_ms": ctx.last_gpu_ms()}
+            if cv2 is not None:
+                r["cv2_ms"] = med(lambda: cv2.recoverPose(E, p1, p2, K), 5, 1)
+            print(json.dumps(r))
     if "next" in only:   # candidate min-distance filter (:258) and triangulate_landmarks (:107-206)
         from monocular_visual_odometry_va4mr_b200 import hotpath
         rng = np.random.default_rng(3)

@@ -125,6 +125,16 @@ int b200vo_triangulate_landmarks(b200vo_ctx* ctx, const double K[9], double min_
                                  float* new_landmarks, float* new_keypoints, int* n_new);
 
 /*
+ * Replaces cv2.recoverPose(E, points1, points2, K) at :315 (default distanceThresh = 50):
+ * decomposeEssentialMat + cheirality test of the four (R, +-t) on triangulated points.
+ * E row-major 3x3; p1, p2 float32 (n,2) pixels; R row-major 3x3, t (3); mask uint8 (n), 0 / 255 as
+ * cv2 writes it; *n_good = cv2's return value (points passing the test for the chosen pose).
+ */
+int b200vo_recover_pose(b200vo_ctx* ctx, const double E[9], const float* p1, const float* p2, int n,
+                        const double K[9], double distance_thresh, double R[9], double t[3],
+                        uint8_t* mask, int* n_good);
+
+/*
  * Replaces cv2.solvePnPRansac(obj, img, K, zeros(4), flags=SOLVEPNP_P3P, confidence=,
  * reprojectionError=, iterationsCount=) at :343 (incl. cv2's EPnP refit on the inliers).
  * obj float32 (n,3), img float32 (n,2).  inliers int32 (n) caller-allocated, ascending,

@@ -275,6 +275,32 @@ def findEssentialMat(points1, points2, cameraMatrix=None, method=RANSAC, prob=0.
 
 
 # --------------------------------------------------------------------------------------
+# cv2.recoverPose  (reference :315)
+# --------------------------------------------------------------------------------------
+def recoverPose(E, points1, points2, cameraMatrix=None, R=None, t=None, mask=None, distanceThresh=50.0):
+    """cv2.recoverPose(E, points1, points2, K) -> (retval, R (3,3), t (3,1), mask (n,1) uint8 0/255)."""
+    if cameraMatrix is None or R is not None or t is not None or mask is not None:
+        raise NotImplementedError("b200vo recoverPose: only (E, points1, points2, cameraMatrix[, distanceThresh=]) (reference :315)")
+    Em = np.ascontiguousarray(np.asarray(E, np.float64).reshape(3, 3))
+    p1 = np.ascontiguousarray(np.asarray(points1, np.float32).reshape(-1, 2))
+    p2 = np.ascontiguousarray(np.asarray(points2, np.float32).reshape(-1, 2))
+    if p1.shape != p2.shape:
+        raise error("b200vo recoverPose: (-215:Assertion failed) npoints >= 0 && points2.checkVector(2) == npoints")
+    n = p1.shape[0]
+    K = np.ascontiguousarray(np.asarray(cameraMatrix, np.float64).reshape(3, 3))
+    Ro = np.zeros((3, 3), np.float64)
+    to = np.zeros((3, 1), np.float64)
+    m = np.zeros((n, 1), np.uint8)
+    good = C.c_int(0)
+    ctx = _ctx()
+    rc = ctx.lib.b200vo_recover_pose(ctx.h, _p(Em, c_f64p), _p(p1, c_f32p), _p(p2, c_f32p), n, _p(K, c_f64p), float(distanceThresh),
+                                     _p(Ro, c_f64p), _p(to, c_f64p), _p(m, c_u8p), C.byref(good))
+    if rc != 0:
+        _raise(ctx, rc, "recoverPose")
+    return good.value, Ro, to, m
+
+
+# --------------------------------------------------------------------------------------
 # cv2.solvePnPRansac  (reference :343)
 # --------------------------------------------------------------------------------------
 def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, rvec=None, tvec=None,
@@ -310,7 +336,7 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, rvec=Non
 # --------------------------------------------------------------------------------------
 # installation onto the real cv2 module (route (i) of SURVEY.md 8b)
 # --------------------------------------------------------------------------------------
-_PATCHED = ("calcOpticalFlowPyrLK", "goodFeaturesToTrack", "BFMatcher", "findEssentialMat", "solvePnPRansac")
+_PATCHED = ("calcOpticalFlowPyrLK", "goodFeaturesToTrack", "BFMatcher", "findEssentialMat", "solvePnPRansac", "recoverPose")
 _saved: dict = {}
 
 

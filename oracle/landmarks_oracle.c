@@ -109,3 +109,76 @@ int orc_triangulate_landmarks(const double K[9], double min_dist, double max_dis
     *n_new = cnt;
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * f3: cv2.recoverPose(E, points1, points2, K) at reference :315 (OpenCV calib3d five-point.cpp,
+ * 4.13): decomposeEssentialMat (SVD of E by OpenCV's small-matrix Jacobi, det sign fix,
+ * R1 = U W Vt, R2 = U W^T Vt, t = U[:,2]); for the four (R, +-t) the cheirality test on points
+ * triangulated with P0 = [I|0] (cv2.triangulatePoints on K-normalised float64 points):
+ *   Q.z * Q.w > 0,  Q.z/Q.w < 50,  0 < (P Q/Q.w).z < 50;
+ * the pose with the most passing points wins (ties in the order 1, 2, 3, 4); mask is 0 / 255.
+ * ------------------------------------------------------------------------------------------ */
+static void mat3_mul(const double* A, const double* B, double* C)
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+static double det3d(const double* M)
+{
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+void orc_decompose_essential(const double E[9], double R1[9], double R2[9], double t[3])
+{
+    double W[3], U[9], Vt[9], T[9];
+    orc_jacobi_svd(E, 3, 3, W, U, Vt);
+    if (det3d(U) < 0) for (int k = 0; k < 9; ++k) U[k] = -U[k];
+    if (det3d(Vt) < 0) for (int k = 0; k < 9; ++k) Vt[k] = -Vt[k];
+    const double Wm[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1}, Wt[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1};
+    mat3_mul(U, Wm, T); mat3_mul(T, Vt, R1);
+    mat3_mul(U, Wt, T); mat3_mul(T, Vt, R2);
+    t[0] = U[2]; t[1] = U[5]; t[2] = U[8];
+}
+
+int orc_recover_pose(const double E[9], const float* p1, const float* p2, int n, const double K[9],
+                     double dist_thresh, double R[9], double t[3], uint8_t* mask, int* n_good)
+{
+    double R1[9], R2[9], tt[3];
+    orc_decompose_essential(E, R1, R2, tt);
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    int good[4] = {0, 0, 0, 0};
+    uint8_t* masks = mask;   /* caller provides 4*n bytes of scratch after... see wrapper: mask has room for 4n */
+    for (int h = 0; h < 4; ++h) {
+        const double* Rh = (h & 1) ? R2 : R1;
+        const double sg = h < 2 ? 1.0 : -1.0;
+        double P[12];
+        for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) P[4 * i + j] = Rh[3 * i + j]; P[4 * i + 3] = sg * tt[i]; }
+        for (int i = 0; i < n; ++i) {
+            const double x1 = ((double)p1[2 * i] - cx) / fx, y1 = ((double)p1[2 * i + 1] - cy) / fy;
+            const double x2 = ((double)p2[2 * i] - cx) / fx, y2 = ((double)p2[2 * i + 1] - cy) / fy;
+            /* P0 = [I | 0] */
+            double A[16] = {-1, 0, x1, 0, 0, -1, y1, 0, 0, 0, 0, 0, 0, 0, 0, 0}, Wd[4], U[16], Vt[16];
+            for (int k = 0; k < 4; ++k) { A[8 + k] = x2 * P[8 + k] - P[k]; A[12 + k] = y2 * P[8 + k] - P[4 + k]; }
+            orc_jacobi_svd(A, 4, 4, Wd, U, Vt);
+            double Q[4] = {Vt[12], Vt[13], Vt[14], Vt[15]};
+            int ok = Q[2] * Q[3] > 0;
+            Q[0] /= Q[3]; Q[1] /= Q[3]; Q[2] /= Q[3]; Q[3] /= Q[3];
+            ok = ok && (Q[2] < dist_thresh);
+            const double z = P[8] * Q[0] + P[9] * Q[1] + P[10] * Q[2] + P[11] * Q[3];
+            ok = ok && (z > 0) && (z < dist_thresh);
+            masks[(size_t)h * n + i] = ok ? 255 : 0;
+            good[h] += ok;
+        }
+    }
+    int win;
+    if (good[0] >= good[1] && good[0] >= good[2] && good[0] >= good[3]) win = 0;
+    else if (good[1] >= good[0] && good[1] >= good[2] && good[1] >= good[3]) win = 1;
+    else if (good[2] >= good[0] && good[2] >= good[1] && good[2] >= good[3]) win = 2;
+    else win = 3;
+    const double* Rw = (win & 1) ? R2 : R1;
+    for (int k = 0; k < 9; ++k) R[k] = Rw[k];
+    for (int k = 0; k < 3; ++k) t[k] = win < 2 ? tt[k] : -tt[k];
+    if (win != 0) memmove(mask, masks + (size_t)win * n, (size_t)n);
+    *n_good = good[win];
+    return win;
+}

@@ -90,6 +90,12 @@ int orc_triangulate_landmarks(const double K[9], double min_dist, double max_dis
                               const double cur_cw[12], uint8_t* keep, float* new_landmarks,
                               float* new_keypoints, int* n_new);
 
+/* f3, ref :315 cv2.recoverPose(E, p1, p2, K) with the default distanceThresh = 50.  mask must have room
+ * for 4*n bytes (the first n hold the result, 0 / 255).  Returns the index 0..3 of the winning (R, +-t). */
+void orc_decompose_essential(const double E[9], double R1[9], double R2[9], double t[3]);
+int orc_recover_pose(const double E[9], const float* p1, const float* p2, int n, const double K[9],
+                     double dist_thresh, double R[9], double t[3], uint8_t* mask, int* n_good);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,9 +57,9 @@ def main():
                frame_crc=np.array([zlib.crc32(f.tobytes()) for f in frame_list], np.uint32),
                K=s["K"], cv2_version=np.array(cv2.__version__))
     calls = []   # (kind, index within kind)
-    n = dict(klt=0, gftt=0, knn=0, emat=0, pnp=0, tri=0, fadd=0)
+    n = dict(klt=0, gftt=0, knn=0, emat=0, pnp=0, tri=0, fadd=0, rpose=0)
     real = dict(klt=cv2.calcOpticalFlowPyrLK, gftt=cv2.goodFeaturesToTrack, bf=cv2.BFMatcher,
-                emat=cv2.findEssentialMat, pnp=cv2.solvePnPRansac)
+                emat=cv2.findEssentialMat, pnp=cv2.solvePnPRansac, rpose=cv2.recoverPose)
 
     def klt(prev, nxt, pts, nextPts, **kw):
         out = real["klt"](prev, nxt, pts, nextPts, **kw)
@@ -113,6 +113,16 @@ def main():
         rec[f"pnp{i}_ok"] = np.array(out[0]); rec[f"pnp{i}_rvec"] = out[1]; rec[f"pnp{i}_tvec"] = out[2]
         rec[f"pnp{i}_inliers"] = out[3] if out[3] is not None else np.zeros((0, 1), np.int32)
         calls.append(("pnp", i))
+        return out
+
+    def rpose(E, p1, p2, K):                    # :315, "next" row f3
+        out = real["rpose"](E, p1, p2, K)
+        i = n["rpose"]; n["rpose"] += 1
+        rec[f"rpose{i}_E"] = np.array(E, copy=True); rec[f"rpose{i}_p1"] = np.array(p1, copy=True); rec[f"rpose{i}_p2"] = np.array(p2, copy=True)
+        # copies: the reference flips t in place right after the call (:317)
+        rec[f"rpose{i}_good"] = np.array(out[0]); rec[f"rpose{i}_R"] = np.array(out[1], copy=True)
+        rec[f"rpose{i}_t"] = np.array(out[2], copy=True); rec[f"rpose{i}_mask"] = np.array(out[3], copy=True)
+        calls.append(("rpose", i))
         return out
 
     # ---- the two "next" rows of SURVEY.md 8f, recorded at method level (they are numpy, not cv2 calls) ----
@@ -170,7 +180,7 @@ def main():
                                OPTIONS['min_baseline_frames']], np.float64)
 
     cv2.calcOpticalFlowPyrLK, cv2.goodFeaturesToTrack, cv2.BFMatcher = klt, gftt, Matcher
-    cv2.findEssentialMat, cv2.solvePnPRansac = emat, pnp
+    cv2.findEssentialMat, cv2.solvePnPRansac, cv2.recoverPose = emat, pnp, rpose
     try:
         vo = VisualOdometryPipeLine(s["K"], OPTIONS)
         b0, b1 = RENDER["bootstrap"]
@@ -179,7 +189,7 @@ def main():
             vo.continuous_operation(frame_list[i])
     finally:
         cv2.calcOpticalFlowPyrLK, cv2.goodFeaturesToTrack, cv2.BFMatcher = real["klt"], real["gftt"], real["bf"]
-        cv2.findEssentialMat, cv2.solvePnPRansac = real["emat"], real["pnp"]
+        cv2.findEssentialMat, cv2.solvePnPRansac, cv2.recoverPose = real["emat"], real["pnp"], real["rpose"]
         VisualOdometryPipeLine.triangulate_landmarks, VisualOdometryPipeLine.feature_adding = orig_tri, orig_add
     rec["calls"] = np.array([f"{k}{i}" for k, i in calls])
     rec["num_pts"] = np.array(vo.num_pts)

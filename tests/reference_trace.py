@@ -81,9 +81,16 @@ def check_fadd(g, i, run):
     assert np.array_equal(valid, g[f"fadd{i}_valid"].astype(bool)), f"fadd{i}"
 
 
+def check_rpose(g, i, run):
+    good, R, t, mask = run(g[f"rpose{i}_E"], g[f"rpose{i}_p1"], g[f"rpose{i}_p2"], g["K"])
+    assert int(good) == int(g[f"rpose{i}_good"]), f"rpose{i}: count"
+    assert np.array_equal(np.asarray(mask).ravel(), g[f"rpose{i}_mask"].ravel()), f"rpose{i}: mask"
+    assert np.abs(R - g[f"rpose{i}_R"]).max() < 1e-12 and np.abs(np.ravel(t) - g[f"rpose{i}_t"].ravel()).max() < 1e-12
+
+
 def replay(impl):
     g, frames = load()
-    seen = dict(klt=0, gftt=0, knn=0, emat=0, pnp=0, tri=0, fadd=0)
+    seen = dict(klt=0, gftt=0, knn=0, emat=0, pnp=0, tri=0, fadd=0, rpose=0)
     for name in g["calls"]:
         name = str(name)
         kind, i = name.rstrip("0123456789"), int(name[len(name.rstrip("0123456789")):])
@@ -102,6 +109,8 @@ def replay(impl):
             check_tri(g, i, impl.tri)
         elif kind == "fadd":
             check_fadd(g, i, impl.fadd)
+        elif kind == "rpose":
+            check_rpose(g, i, impl.rpose)
     assert seen["klt"] >= 2 and seen["gftt"] >= 1 and seen["knn"] == 1 and seen["emat"] == 1 and seen["pnp"] >= 1
-    assert seen["tri"] >= 2 and seen["fadd"] >= 1
+    assert seen["tri"] >= 2 and seen["fadd"] >= 1 and seen["rpose"] == 1
     return seen

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from monocular_visual_odometry_va4mr_b200 import hotpath
+from monocular_visual_odometry_va4mr_b200 import cv2_compat, hotpath
 
 pytestmark = pytest.mark.gpu
 OPT = lambda cfg: dict(min_dist_landmarks=cfg[0], max_dist_landmarks=cfg[1], min_baseline_angle=cfg[2], min_baseline_frames=int(cfg[3]))
@@ -68,3 +68,29 @@ def test_triangulate_edges():
     with pytest.raises(Exception):
         hotpath.triangulate_landmarks(K, dict(opt, min_baseline_frames=-5), pts, pts, np.full(3, 7), [(np.eye(3), np.zeros((3, 1)))],
                                       np.eye(3), np.zeros((3, 1)))
+
+
+def test_recover_pose_vs_oracle_and_live_cv2(g):
+    """ref :315 through the cv2-shaped shim: count, 0/255 mask and (R, t) vs the oracle, the recorded call and live cv2."""
+    import sys
+    import oracle
+    sys.path.insert(0, GOLDEN)
+    from make_golden import make_emat_pair
+    good, R, t, mask = cv2_compat.recoverPose(g["rpose0_E"], g["rpose0_p1"], g["rpose0_p2"], g["K"])
+    assert good == int(g["rpose0_good"]) and np.array_equal(mask, g["rpose0_mask"]) and mask.shape == g["rpose0_mask"].shape
+    assert R.shape == (3, 3) and t.shape == (3, 1) and np.abs(R - g["rpose0_R"]).max() < 1e-12 and np.abs(t - g["rpose0_t"]).max() < 1e-12
+    for n, of, seed in ((600, 0.2, 7), (2500, 0.3, 40), (300, 0.6, 3), (50, 0.0, 9), (5, 0.0, 2)):
+        p1, p2, K = make_emat_pair(n, of, seed)
+        E, _ = cv2_compat.findEssentialMat(p1, p2, K, method=cv2_compat.RANSAC, prob=0.99, threshold=1)
+        good, R, t, mask = cv2_compat.recoverPose(E, p1, p2, K)
+        go, Ro, to, mo = oracle.recover_pose(E, p1, p2, K)
+        assert good == go and np.array_equal(mask, mo)
+        assert np.abs(R - Ro).max() < 1e-14 and np.abs(t - to).max() < 1e-14     # same algorithm; libm hypot/sqrt may differ in the last bit
+        try:
+            import cv2
+        except ImportError:
+            continue
+        gc, Rc, tc, mc = cv2.recoverPose(E, p1, p2, K)
+        assert good == gc and np.array_equal(mask, mc) and np.abs(R - Rc).max() < 1e-12 and np.abs(t - tc).max() < 1e-12
+    with pytest.raises(NotImplementedError):
+        cv2_compat.recoverPose(E, p1, p2)

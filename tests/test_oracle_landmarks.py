@@ -85,3 +85,19 @@ def test_triangulate_points_vs_live_cv2():
             assert np.all(np.abs(lm[k] - L) <= np.spacing(np.abs(L))), i
             k += 1
     assert k == len(lm) and k > 200
+
+
+def test_recover_pose_vs_live_cv2():
+    """ref :315 -- count, mask (0/255) and the chosen (R, t) as cv2.recoverPose returns them."""
+    cv2 = pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden import make_emat_pair
+    for n, of, seed in ((600, 0.2, 7), (2500, 0.3, 40), (300, 0.6, 3), (50, 0.0, 9), (8, 0.0, 1)):
+        p1, p2, K = make_emat_pair(n, of, seed)
+        E, m = cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.99, threshold=1)
+        E = E[:3]
+        good, R, t, mask = cv2.recoverPose(E, p1, p2, K)
+        go, Ro, to, mo = oracle.recover_pose(E, p1, p2, K)
+        assert go == good and np.array_equal(mo, mask) and mo.dtype == np.uint8
+        assert np.abs(R - Ro).max() < 1e-12 and np.abs(t - to).max() < 1e-12

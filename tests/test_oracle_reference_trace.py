@@ -29,6 +29,7 @@ def _pnp(obj, img, K, iters, err, conf):
 
 def test_oracle_replays_reference_trace():
     impl = SimpleNamespace(klt=_klt, gftt=lambda img, mc, q, md, bs: oracle.good_features_to_track(img, mc, q, md, bs),
-                           knn=_knn, emat=_emat, pnp=_pnp, tri=oracle.triangulate_landmarks, fadd=oracle.min_distance_mask)
+                           knn=_knn, emat=_emat, pnp=_pnp, tri=oracle.triangulate_landmarks, fadd=oracle.min_distance_mask,
+                           rpose=oracle.recover_pose)
     seen = reference_trace.replay(impl)
     assert sum(seen.values()) >= 10

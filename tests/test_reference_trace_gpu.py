@@ -43,5 +43,6 @@ def _tri(K, cfg, first_keys, keys, first_pose, poses, cur):                     
 
 def test_cuda_replays_reference_trace():
     seen = reference_trace.replay(SimpleNamespace(klt=_klt, gftt=_gftt, knn=_knn, emat=_emat, pnp=_pnp, tri=_tri,
-                                                  fadd=hotpath.min_distance_mask))                             # :258
+                                                  fadd=hotpath.min_distance_mask,                              # :258
+                                                  rpose=cv2_compat.recoverPose))                               # :315
     assert sum(seen.values()) >= 10
