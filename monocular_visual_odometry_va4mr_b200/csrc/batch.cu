@@ -42,6 +42,10 @@ struct b200vo_batch {
     cudaEvent_t chunk_ev[B200VO_BATCH_CHUNKS];
     cudaEvent_t done_ev = nullptr;
     cudaStream_t io_stream = nullptr;      // landmark upload / KLT result read-back beside the kernels
+    // PnP is a chain of small latency-bound kernels that needs the LANDMARK tracks only: it runs on a
+    // high-priority stream beside the candidate tracker (which fills the SMs) instead of after it
+    cudaStream_t pose_stream = nullptr;
+    cudaEvent_t lm_ev = nullptr, cand_ev = nullptr, pose_ev = nullptr;
     cudaEvent_t obj_ev = nullptr, klt_ev = nullptr, io_ev = nullptr;
     // optional per-kernel timing (CUDA events on the ctx stream): [step][stage] boundaries
     bool profile = false;
@@ -148,7 +152,12 @@ extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batc
     for (auto& e : B->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&B->done_ev, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&B->io_stream, cudaStreamNonBlocking);
-    for (cudaEvent_t* e : {&B->obj_ev, &B->klt_ev, &B->io_ev}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    for (cudaEvent_t* e : {&B->obj_ev, &B->klt_ev, &B->io_ev, &B->lm_ev, &B->cand_ev, &B->pose_ev}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaStreamCreateWithPriority(&B->pose_stream, cudaStreamNonBlocking, greatest);
+    }
     for (auto& e : B->q_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&B->step_end_ev, cudaEventDisableTiming);
     uint8_t* p = (uint8_t*)B->work.p;
@@ -181,7 +190,8 @@ extern "C" void b200vo_batch_destroy(b200vo_batch* B)
         for (auto& e : B->chunk_ev) cudaEventDestroy(e);
         cudaEventDestroy(B->done_ev);
         cudaStreamSynchronize(B->io_stream); cudaStreamDestroy(B->io_stream);
-        for (cudaEvent_t e : {B->obj_ev, B->klt_ev, B->io_ev}) cudaEventDestroy(e);
+        for (cudaEvent_t e : {B->obj_ev, B->klt_ev, B->io_ev, B->lm_ev, B->cand_ev, B->pose_ev}) cudaEventDestroy(e);
+        cudaStreamSynchronize(B->pose_stream); cudaStreamDestroy(B->pose_stream);
     }
     delete B;
 }
@@ -286,25 +296,31 @@ extern "C" int b200vo_batch_prime(b200vo_batch* B, const uint8_t* frames)
 // device-resident core: everything after the new frames are in `frames_dev`
 // pyramids of the new frames + KLT for sequences [b0, b0 + nb)
 // (frames_dev == nullptr: the pyramids of set B->nxt were built ahead by b200vo_batch_submit_frames)
+// which: 0 = both point sets in one launch, 1 = pyramids + landmark set only, 2 = candidate set only
 static int batch_track(b200vo_batch* B, int b0, int nb, const uint8_t* frames_dev, const float* lm_pts, const int* n_lm,
                        const float* cand_pts, const int* n_cand, float* lm_next, uint8_t* lm_status, float* cand_next,
-                       uint8_t* cand_status)
+                       uint8_t* cand_status, int which = 0)
 {
     b200vo_ctx* ctx = B->ctx;
     const b200vo_batch_cfg& c = B->cfg;
     const int nxt = B->nxt;
     const size_t fb = (size_t)c.rows * c.cols, sb = B->geom.slab_bytes;
     const int L = c.max_landmarks, Cn = c.max_candidates;
-    if (b0 == 0) prof_mark(B, 0);
-    if (frames_dev)
-        VO_TRY(vo_build_pyramids(ctx, frames_dev + (size_t)b0 * fb, fb, c.rows, c.cols, B->geom,
-                                 (uint8_t*)B->slabs[nxt].p + (size_t)b0 * sb, sb, nb));
-    if (b0 == 0 && nb == B->batch) prof_mark(B, 1);
+    if (which != 2) {
+        if (b0 == 0) prof_mark(B, 0);
+        if (frames_dev)
+            VO_TRY(vo_build_pyramids(ctx, frames_dev + (size_t)b0 * fb, fb, c.rows, c.cols, B->geom,
+                                     (uint8_t*)B->slabs[nxt].p + (size_t)b0 * sb, sb, nb));
+        if (b0 == 0 && nb == B->batch) prof_mark(B, 1);
+    }
     KltPointSet sets[2] = {{L, n_lm + b0, lm_pts + (size_t)b0 * L * 2, lm_next + (size_t)b0 * L * 2, lm_status + (size_t)b0 * L, nullptr},
                            {Cn, n_cand + b0, cand_pts + (size_t)b0 * Cn * 2, cand_next + (size_t)b0 * Cn * 2,
                             cand_status + (size_t)b0 * Cn, nullptr}};
+    if (which == 2 && Cn <= 0) return 0;
+    const KltPointSet* first = which == 2 ? sets + 1 : sets;
+    const int n_sets = which == 0 ? (Cn > 0 ? 2 : 1) : 1;
     VO_TRY(vo_klt_launch2(ctx, B->geom, (const uint8_t*)B->slabs[B->cur].p + (size_t)b0 * sb, sb,
-                          (const uint8_t*)B->slabs[nxt].p + (size_t)b0 * sb, sb, nb, sets, Cn > 0 ? 2 : 1, 0, B->kp));
+                          (const uint8_t*)B->slabs[nxt].p + (size_t)b0 * sb, sb, nb, first, n_sets, 0, B->kp));
     return 0;
 }
 
@@ -335,8 +351,39 @@ static int batch_pose(b200vo_batch* B, const float* lm_obj, const int* n_lm, con
     prof_mark(B, 3);
     if (B->profile && B->prof_n < B200VO_PROF_RING) B->prof_n++;
     VO_CUDA(ctx, cudaGetLastError());
-    VO_CUDA(ctx, cudaEventRecord(B->step_end_ev, ctx->stream));
+    return 0;
+}
+
+// the step's kernels are all enqueued (and joined on the ctx stream): the new frames become the previous ones
+static int batch_finish(b200vo_batch* B)
+{
+    VO_CUDA(B->ctx, cudaEventRecord(B->step_end_ev, B->ctx->stream));
     B->cur = B->nxt;
+    return 0;
+}
+
+// Whole-batch step with the pose chain beside the candidate tracker:
+//   ctx stream:   [pyramids] [KLT landmarks] (lm_ev) [KLT candidates] (cand_ev) ........ wait(pose_ev)
+//   pose stream:                     wait(lm_ev) [compact][P3P-RANSAC][EPnP][mask] (pose_ev)
+static int batch_track_pose_overlapped(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts, const float* lm_obj,
+                                       const int* n_lm, const float* cand_pts, const int* n_cand, float* lm_next,
+                                       uint8_t* lm_status, float* cand_next, uint8_t* cand_status, double* pose,
+                                       uint8_t* pnp_ok, uint8_t* inlier_mask, int* n_inliers, cudaEvent_t obj_ready)
+{
+    b200vo_ctx* ctx = B->ctx;
+    cudaStream_t main_stream = ctx->stream;
+    VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status, 1));
+    VO_CUDA(ctx, cudaEventRecord(B->lm_ev, main_stream));
+    VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status, 2));
+    VO_CUDA(ctx, cudaEventRecord(B->cand_ev, main_stream));
+    VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->lm_ev, 0));
+    if (obj_ready) VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, obj_ready, 0));
+    ctx->stream = B->pose_stream;
+    const int rc = batch_pose(B, lm_obj, n_lm, lm_next, lm_status, pose, pnp_ok, inlier_mask, n_inliers);
+    ctx->stream = main_stream;
+    if (rc) return rc;
+    VO_CUDA(ctx, cudaEventRecord(B->pose_ev, B->pose_stream));
+    VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->pose_ev, 0));
     return 0;
 }
 
@@ -349,8 +396,9 @@ static int batch_core(b200vo_batch* B, const uint8_t* frames_dev, const float* l
     if (!B->primed) return vo_set_err(B->ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
     if (!frames_dev) return vo_set_err(B->ctx, B200VO_E_BADARG, "null pointer");
     B->nxt = batch_free_set(B);
-    VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status));
-    return batch_pose(B, lm_obj, n_lm, lm_next, lm_status, pose, pnp_ok, inlier_mask, n_inliers);
+    VO_TRY(batch_track_pose_overlapped(B, frames_dev, lm_pts, lm_obj, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next,
+                                       cand_status, pose, pnp_ok, inlier_mask, n_inliers, nullptr));
+    return batch_finish(B);
 }
 
 extern "C" int b200vo_batch_step_dev(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts_dev,
@@ -452,30 +500,39 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     }
     uint8_t* dq = (uint8_t*)B->outs.p;
     cudaStream_t main_stream = ctx->stream;
-    int rc_chunks = 0;
-    for (int k = 0; k < nchunks && !rc_chunks; ++k) {
-        const int b0 = k * per, n_here = (b0 + per <= nb ? per : nb - b0);
-        if (n_here <= 0) break;
-        cudaStream_t cs = nchunks > 1 ? B->chunk_stream[k % B200VO_BATCH_STREAMS] : main_stream;
-        if (nchunks > 1) VO_CUDA(ctx, cudaStreamWaitEvent(cs, B->done_ev, 0));
-        if (!prefetched)
+    if (prefetched) {
+        // pyramids are already there: landmark tracker, then candidate tracker with the pose chain beside it
+        VO_TRY(batch_track_pose_overlapped(B, nullptr, (const float*)(di + o_lmp), (const float*)(di + o_lmo), (const int*)(di + o_nlm),
+                                           (const float*)(di + o_cp), (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms,
+                                           (float*)(dq + q_cn), dq + q_cs, (double*)(dq + q_pose), dq + q_ok, dq + q_mask,
+                                           (int*)(dq + q_ni), B->obj_ev));
+    } else {
+        int rc_chunks = 0;
+        for (int k = 0; k < nchunks && !rc_chunks; ++k) {
+            const int b0 = k * per, n_here = (b0 + per <= nb ? per : nb - b0);
+            if (n_here <= 0) break;
+            cudaStream_t cs = nchunks > 1 ? B->chunk_stream[k % B200VO_BATCH_STREAMS] : main_stream;
+            if (nchunks > 1) VO_CUDA(ctx, cudaStreamWaitEvent(cs, B->done_ev, 0));
             VO_CUDA(ctx, cudaMemcpyAsync((uint8_t*)B->raw.p + (size_t)b0 * fb, fsrc + (size_t)b0 * fb, (size_t)n_here * fb,
                                          cudaMemcpyHostToDevice, cs));
-        ctx->stream = cs;   // the launch helpers enqueue on ctx->stream
-        rc_chunks = batch_track(B, b0, n_here, prefetched ? nullptr : (const uint8_t*)B->raw.p, (const float*)(di + o_lmp), (const int*)(di + o_nlm),
-                                (const float*)(di + o_cp), (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms,
-                                (float*)(dq + q_cn), dq + q_cs);
-        ctx->stream = main_stream;
-        if (!rc_chunks && nchunks > 1) {
-            VO_CUDA(ctx, cudaEventRecord(B->chunk_ev[k], cs));
-            VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->chunk_ev[k], 0));
+            ctx->stream = cs;   // the launch helpers enqueue on ctx->stream
+            rc_chunks = batch_track(B, b0, n_here, (const uint8_t*)B->raw.p, (const float*)(di + o_lmp), (const int*)(di + o_nlm),
+                                    (const float*)(di + o_cp), (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms,
+                                    (float*)(dq + q_cn), dq + q_cs);
+            ctx->stream = main_stream;
+            if (!rc_chunks && nchunks > 1) {
+                VO_CUDA(ctx, cudaEventRecord(B->chunk_ev[k], cs));
+                VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->chunk_ev[k], 0));
+            }
         }
+        if (rc_chunks) return rc_chunks;
+        VO_CUDA(ctx, cudaEventRecord(B->lm_ev, ctx->stream));      // every chunk's tracks (both point sets) are done
+        VO_CUDA(ctx, cudaEventRecord(B->cand_ev, ctx->stream));
+        VO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B->obj_ev, 0));
+        VO_TRY(batch_pose(B, (const float*)(di + o_lmo), (const int*)(di + o_nlm), (const float*)(dq + q_lmn), dq + q_lms,
+                          (double*)(dq + q_pose), dq + q_ok, dq + q_mask, (int*)(dq + q_ni)));
     }
-    if (rc_chunks) return rc_chunks;
-    VO_CUDA(ctx, cudaEventRecord(B->klt_ev, ctx->stream));
-    VO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B->obj_ev, 0));
-    VO_TRY(batch_pose(B, (const float*)(di + o_lmo), (const int*)(di + o_nlm), (const float*)(dq + q_lmn), dq + q_lms,
-                      (double*)(dq + q_pose), dq + q_ok, dq + q_mask, (int*)(dq + q_ni)));
+    VO_TRY(batch_finish(B));
     uint8_t* ho = hp + in_bytes;
     struct OutCopy { void* dst; size_t off, bytes; bool staged; };
     OutCopy outs[8] = {{lm_next, q_lmn, (size_t)nb * L * 8, false}, {lm_status, q_lms, (size_t)nb * L, false},
@@ -484,9 +541,10 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
                        {pose, q_pose, (size_t)nb * 48, false}, {pnp_ok, q_ok, (size_t)nb, false},
                        {inlier_mask, q_mask, (size_t)nb * L, false}, {n_inliers, q_ni, (size_t)nb * 4, false}};
     // the tracker's results go home on the io stream while PnP runs; the pose results follow PnP
-    VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->klt_ev, 0));
+    VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->lm_ev, 0));
     for (int i = 0; i < 8; ++i) {
         OutCopy& o = outs[i];
+        if (i == 2) VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->cand_ev, 0));
         if (!o.dst || o.bytes == 0) continue;
         o.staged = !is_pinned(o.dst);
         VO_CUDA(ctx, cudaMemcpyAsync(o.staged ? (void*)(ho + o.off) : o.dst, dq + o.off, o.bytes, cudaMemcpyDeviceToHost,
