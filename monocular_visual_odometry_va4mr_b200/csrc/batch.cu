@@ -7,7 +7,7 @@
 #include "internal.cuh"
 #include "pnp.cuh"
 
-#define B200VO_BATCH_CHUNKS 8
+#define B200VO_BATCH_CHUNKS 4
 // Streams are a scarce resource: the driver multiplexes them onto 8 hardware queues by default
 // (CUDA_DEVICE_MAX_CONNECTIONS) and two streams on one queue serialise.  Chunks share 4 streams.
 #define B200VO_BATCH_STREAMS 4
@@ -40,6 +40,7 @@ struct b200vo_batch {
     // host-input path: frames arrive chunk by chunk on a copy stream while earlier chunks are tracked
     cudaStream_t chunk_stream[B200VO_BATCH_STREAMS] = {};  // chunk k: H2D -> pyramid -> KLT on stream k % STREAMS
     cudaEvent_t chunk_ev[B200VO_BATCH_CHUNKS];
+    cudaEvent_t copy_ev[B200VO_BATCH_CHUNKS];   // chunk k's frames have landed (copies run back to back on pre_stream)
     cudaEvent_t done_ev = nullptr;
     cudaStream_t io_stream = nullptr;      // landmark upload / KLT result read-back beside the kernels
     // PnP is a chain of small latency-bound kernels that needs the LANDMARK tracks only: it runs on a
@@ -150,6 +151,7 @@ extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batc
     cudaStreamCreateWithFlags(&B->pre_stream, cudaStreamNonBlocking);
     for (auto& st : B->chunk_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     for (auto& e : B->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& e : B->copy_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&B->done_ev, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&B->io_stream, cudaStreamNonBlocking);
     for (cudaEvent_t* e : {&B->obj_ev, &B->klt_ev, &B->io_ev, &B->lm_ev, &B->cand_ev, &B->pose_ev}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
@@ -188,6 +190,7 @@ extern "C" void b200vo_batch_destroy(b200vo_batch* B)
     if (B->chunk_stream[0]) {
         for (auto& st : B->chunk_stream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
         for (auto& e : B->chunk_ev) cudaEventDestroy(e);
+        for (auto& e : B->copy_ev) cudaEventDestroy(e);
         cudaEventDestroy(B->done_ev);
         cudaStreamSynchronize(B->io_stream); cudaStreamDestroy(B->io_stream);
         for (cudaEvent_t e : {B->obj_ev, B->klt_ev, B->io_ev, B->lm_ev, B->cand_ev, B->pose_ev}) cudaEventDestroy(e);
@@ -296,7 +299,8 @@ extern "C" int b200vo_batch_prime(b200vo_batch* B, const uint8_t* frames)
 // device-resident core: everything after the new frames are in `frames_dev`
 // pyramids of the new frames + KLT for sequences [b0, b0 + nb)
 // (frames_dev == nullptr: the pyramids of set B->nxt were built ahead by b200vo_batch_submit_frames)
-// which: 0 = both point sets in one launch, 1 = pyramids + landmark set only, 2 = candidate set only
+// which: 0 = pyramids + both point sets in one launch, 1 = landmark set only, 2 = candidate set only, 3 = pyramids only,
+// 4 = pyramids + landmark set
 static int batch_track(b200vo_batch* B, int b0, int nb, const uint8_t* frames_dev, const float* lm_pts, const int* n_lm,
                        const float* cand_pts, const int* n_cand, float* lm_next, uint8_t* lm_status, float* cand_next,
                        uint8_t* cand_status, int which = 0)
@@ -306,7 +310,7 @@ static int batch_track(b200vo_batch* B, int b0, int nb, const uint8_t* frames_de
     const int nxt = B->nxt;
     const size_t fb = (size_t)c.rows * c.cols, sb = B->geom.slab_bytes;
     const int L = c.max_landmarks, Cn = c.max_candidates;
-    if (which != 2) {
+    if (which == 0 || which == 3 || which == 4) {
         if (b0 == 0) prof_mark(B, 0);
         if (frames_dev)
             VO_TRY(vo_build_pyramids(ctx, frames_dev + (size_t)b0 * fb, fb, c.rows, c.cols, B->geom,
@@ -316,9 +320,9 @@ static int batch_track(b200vo_batch* B, int b0, int nb, const uint8_t* frames_de
     KltPointSet sets[2] = {{L, n_lm + b0, lm_pts + (size_t)b0 * L * 2, lm_next + (size_t)b0 * L * 2, lm_status + (size_t)b0 * L, nullptr},
                            {Cn, n_cand + b0, cand_pts + (size_t)b0 * Cn * 2, cand_next + (size_t)b0 * Cn * 2,
                             cand_status + (size_t)b0 * Cn, nullptr}};
-    if (which == 2 && Cn <= 0) return 0;
+    if (which == 3 || (which == 2 && Cn <= 0)) return 0;
     const KltPointSet* first = which == 2 ? sets + 1 : sets;
-    const int n_sets = which == 0 ? (Cn > 0 ? 2 : 1) : 1;
+    const int n_sets = which == 0 ? (Cn > 0 ? 2 : 1) : 1;   // which 1, 4: landmark set; 2: candidate set
     VO_TRY(vo_klt_launch2(ctx, B->geom, (const uint8_t*)B->slabs[B->cur].p + (size_t)b0 * sb, sb,
                           (const uint8_t*)B->slabs[nxt].p + (size_t)b0 * sb, sb, nb, first, n_sets, 0, B->kp));
     return 0;
@@ -362,9 +366,13 @@ static int batch_finish(b200vo_batch* B)
     return 0;
 }
 
-// Whole-batch step with the pose chain beside the candidate tracker:
-//   ctx stream:   [pyramids] [KLT landmarks] (lm_ev) [KLT candidates] (cand_ev) ........ wait(pose_ev)
-//   pose stream:                     wait(lm_ev) [compact][P3P-RANSAC][EPnP][mask] (pose_ev)
+// Whole-batch step.  The pose chain needs the LANDMARK tracks only, and it is a string of small
+// latency-bound kernels, while the tracker fills every SM: landmark tracker + pose chain go to a
+// high-priority stream, the candidate tracker to the ctx stream, so that the landmark CTAs are
+// dispatched first, the candidate CTAs fill the machine behind them (no idle tail between the two
+// launches) and the pose kernels slip in as soon as they are ready.
+//   ctx stream:   [pyramids] (pyr_ev) [KLT candidates] (cand_ev) .................... wait(pose_ev)
+//   pose stream:       wait(pyr_ev) [KLT landmarks] (lm_ev) [compact][P3P-RANSAC][EPnP][mask] (pose_ev)
 static int batch_track_pose_overlapped(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts, const float* lm_obj,
                                        const int* n_lm, const float* cand_pts, const int* n_cand, float* lm_next,
                                        uint8_t* lm_status, float* cand_next, uint8_t* cand_status, double* pose,
@@ -372,17 +380,19 @@ static int batch_track_pose_overlapped(b200vo_batch* B, const uint8_t* frames_de
 {
     b200vo_ctx* ctx = B->ctx;
     cudaStream_t main_stream = ctx->stream;
-    VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status, 1));
-    VO_CUDA(ctx, cudaEventRecord(B->lm_ev, main_stream));
+    VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status, 3));
+    VO_CUDA(ctx, cudaEventRecord(B->klt_ev, main_stream));          // pyramids and every input of the step are in place
+    VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->klt_ev, 0));
+    ctx->stream = B->pose_stream;
+    int rc = batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status, 1);
+    if (!rc) rc = (int)cudaEventRecord(B->lm_ev, B->pose_stream);
+    if (!rc && obj_ready) rc = (int)cudaStreamWaitEvent(B->pose_stream, obj_ready, 0);
+    if (!rc) rc = batch_pose(B, lm_obj, n_lm, lm_next, lm_status, pose, pnp_ok, inlier_mask, n_inliers);
+    ctx->stream = main_stream;
+    if (rc) return rc < 0 ? rc : vo_cuda_fail(ctx, (cudaError_t)rc, "pose stream");
+    VO_CUDA(ctx, cudaEventRecord(B->pose_ev, B->pose_stream));
     VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status, 2));
     VO_CUDA(ctx, cudaEventRecord(B->cand_ev, main_stream));
-    VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->lm_ev, 0));
-    if (obj_ready) VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, obj_ready, 0));
-    ctx->stream = B->pose_stream;
-    const int rc = batch_pose(B, lm_obj, n_lm, lm_next, lm_status, pose, pnp_ok, inlier_mask, n_inliers);
-    ctx->stream = main_stream;
-    if (rc) return rc;
-    VO_CUDA(ctx, cudaEventRecord(B->pose_ev, B->pose_stream));
     VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->pose_ev, 0));
     return 0;
 }
@@ -507,18 +517,31 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
                                            (float*)(dq + q_cn), dq + q_cs, (double*)(dq + q_pose), dq + q_ok, dq + q_mask,
                                            (int*)(dq + q_ni), B->obj_ev));
     } else {
+        // The frames go up chunk by chunk, back to back on the copy stream; chunk k's pyramids + landmark tracker
+        // run on a compute stream as soon as its frames have landed (the later chunks are on the wire meanwhile);
+        // then the candidate tracker for the whole batch on the ctx stream with the pose chain beside it.
         int rc_chunks = 0;
+        if (nchunks > 1) {
+            VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->step_end_ev, 0));   // B->raw is free again
+            VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->done_ev, 0));       // behind the step's small uploads
+            for (int k = 0; k < nchunks; ++k) {
+                const int b0 = k * per, n_here = (b0 + per <= nb ? per : nb - b0);
+                if (n_here <= 0) break;
+                VO_CUDA(ctx, cudaMemcpyAsync((uint8_t*)B->raw.p + (size_t)b0 * fb, fsrc + (size_t)b0 * fb, (size_t)n_here * fb,
+                                             cudaMemcpyHostToDevice, B->pre_stream));
+                VO_CUDA(ctx, cudaEventRecord(B->copy_ev[k], B->pre_stream));
+            }
+        }
         for (int k = 0; k < nchunks && !rc_chunks; ++k) {
             const int b0 = k * per, n_here = (b0 + per <= nb ? per : nb - b0);
             if (n_here <= 0) break;
             cudaStream_t cs = nchunks > 1 ? B->chunk_stream[k % B200VO_BATCH_STREAMS] : main_stream;
-            if (nchunks > 1) VO_CUDA(ctx, cudaStreamWaitEvent(cs, B->done_ev, 0));
-            VO_CUDA(ctx, cudaMemcpyAsync((uint8_t*)B->raw.p + (size_t)b0 * fb, fsrc + (size_t)b0 * fb, (size_t)n_here * fb,
-                                         cudaMemcpyHostToDevice, cs));
+            if (nchunks > 1) VO_CUDA(ctx, cudaStreamWaitEvent(cs, B->copy_ev[k], 0));
+            else VO_CUDA(ctx, cudaMemcpyAsync(B->raw.p, fsrc, (size_t)n_here * fb, cudaMemcpyHostToDevice, cs));
             ctx->stream = cs;   // the launch helpers enqueue on ctx->stream
             rc_chunks = batch_track(B, b0, n_here, (const uint8_t*)B->raw.p, (const float*)(di + o_lmp), (const int*)(di + o_nlm),
                                     (const float*)(di + o_cp), (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms,
-                                    (float*)(dq + q_cn), dq + q_cs);
+                                    (float*)(dq + q_cn), dq + q_cs, 4);
             ctx->stream = main_stream;
             if (!rc_chunks && nchunks > 1) {
                 VO_CUDA(ctx, cudaEventRecord(B->chunk_ev[k], cs));
@@ -526,11 +549,19 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
             }
         }
         if (rc_chunks) return rc_chunks;
-        VO_CUDA(ctx, cudaEventRecord(B->lm_ev, ctx->stream));      // every chunk's tracks (both point sets) are done
-        VO_CUDA(ctx, cudaEventRecord(B->cand_ev, ctx->stream));
-        VO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B->obj_ev, 0));
-        VO_TRY(batch_pose(B, (const float*)(di + o_lmo), (const int*)(di + o_nlm), (const float*)(dq + q_lmn), dq + q_lms,
-                          (double*)(dq + q_pose), dq + q_ok, dq + q_mask, (int*)(dq + q_ni)));
+        VO_CUDA(ctx, cudaEventRecord(B->lm_ev, main_stream));      // every chunk's pyramids and landmark tracks are done
+        VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->lm_ev, 0));
+        VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->obj_ev, 0));
+        ctx->stream = B->pose_stream;
+        const int rc_pose = batch_pose(B, (const float*)(di + o_lmo), (const int*)(di + o_nlm), (const float*)(dq + q_lmn), dq + q_lms,
+                                       (double*)(dq + q_pose), dq + q_ok, dq + q_mask, (int*)(dq + q_ni));
+        ctx->stream = main_stream;
+        if (rc_pose) return rc_pose;
+        VO_CUDA(ctx, cudaEventRecord(B->pose_ev, B->pose_stream));
+        VO_TRY(batch_track(B, 0, nb, nullptr, (const float*)(di + o_lmp), (const int*)(di + o_nlm), (const float*)(di + o_cp),
+                           (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms, (float*)(dq + q_cn), dq + q_cs, 2));
+        VO_CUDA(ctx, cudaEventRecord(B->cand_ev, main_stream));
+        VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->pose_ev, 0));
     }
     VO_TRY(batch_finish(B));
     uint8_t* ho = hp + in_bytes;
