@@ -40,17 +40,20 @@ struct KV2 {
     static constexpr int PER_WARP = 2 * B_PATCH + B_J + 2 * B_DER + B_IWIN;   // two patch buffers (prefetch)
 };
 
+// 16-bit weights x 8-bit pixels.  The weights are SIGNED halves: iw11 = 2^14 - iw00 - iw01 - iw10 is -1
+// when the three rounded weights add up to 2^14 + 1 (a fractional part of ~0 in x or y, about one
+// position in a thousand) -- cv2 carries that -1 through its integer arithmetic, and so must this.
 __device__ __forceinline__ uint32_t dp2a_lo_u(uint32_t a, uint32_t b, uint32_t c)
 {
-    uint32_t d;
-    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
+    return (uint32_t)d;
 }
 __device__ __forceinline__ uint32_t dp2a_hi_u(uint32_t a, uint32_t b, uint32_t c)
 {
-    uint32_t d;
-    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"((int)c));
+    return (uint32_t)d;
 }
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)   // unsigned pixels x signed coefficients
 {
@@ -92,7 +95,7 @@ __device__ __forceinline__ void stage_rows_async(uint8_t* dst, const uint8_t* sr
 
 // 8 interpolated intensities (13-bit, = 32 x grey level) of the run starting at byte offset `off`
 // of `row0` (and the row below it) in a shared-memory image with row stride RS.
-// wt = iw00 | iw01 << 16, wb = iw10 | iw11 << 16.  off & 3 == sh for every lane of the warp.
+// wt = iw00 | iw01 << 16, wb = iw10 | iw11 << 16 (signed 16-bit halves).  off & 3 == sh for every lane of the warp.
 template <int RS>
 __device__ __forceinline__ void interp_run8(const uint8_t* img, int off, int sh8, uint32_t wt, uint32_t wb, int* I)
 {

@@ -135,3 +135,35 @@ def test_prefetched_frames_equal_call_by_call(wl):
     with pytest.raises(B200VOError):
         sb.step(frames[1], wl.lm_pts[0], wl.lm_obj[0], wl.n_lm[0], wl.cand_pts[0], wl.n_cand[0])
     sb.close()
+
+
+@pytest.mark.parametrize("shape,w,h", [("parking", 640, 480), ("malaga", 512, 384)])
+def test_batch_other_shapes_equal_per_call_path(shape, w, h):
+    """The reference's Parking / Malaga options (maxLevel 10 -> 5 or 6 levels, PnP_error 5) through the batched step."""
+    opts = workload.REFERENCE_OPTIONS[shape]
+    wl2 = workload.TrackWorkload(shape, batch=3, n_frames=3, n_landmarks=200, n_candidates=100, n_distinct=2, seed=3,
+                                 width=w, height=h, cap_landmarks=256, cap_candidates=128)
+    order, outs = _run_steps(wl2, 2, opts, pinned=True)
+    for t, o in enumerate(outs):
+        f, g = order[t], order[t + 1]
+        for s in range(wl2.batch):
+            nl, nc = int(wl2.n_lm[f, s]), int(wl2.n_cand[f, s])
+            p, st, _ = cv2_compat.calcOpticalFlowPyrLK(wl2.frames[f, s], wl2.frames[g, s], wl2.lm_pts[f, s, :nl], None,
+                                                       winSize=opts["win"], maxLevel=opts["max_level"], criteria=opts["criteria"])
+            assert np.array_equal(o["lm_status"][s, :nl], st.ravel()) and np.array_equal(o["lm_next"][s, :nl], p)
+            if nc:
+                pc, stc, _ = cv2_compat.calcOpticalFlowPyrLK(wl2.frames[f, s], wl2.frames[g, s], wl2.cand_pts[f, s, :nc], None,
+                                                             winSize=opts["win"], maxLevel=opts["max_level"], criteria=opts["criteria"])
+                assert np.array_equal(o["cand_status"][s, :nc], stc.ravel()) and np.array_equal(o["cand_next"][s, :nc], pc)
+            keep = st.ravel() == 1
+            if keep.sum() < 4:
+                continue
+            ok, rv, tv, inl = cv2_compat.solvePnPRansac(wl2.lm_obj[f, s, :nl][keep], p[keep], wl2.K, np.zeros(4),
+                                                        flags=cv2_compat.SOLVEPNP_P3P, confidence=opts["pnp_conf"],
+                                                        reprojectionError=opts["pnp_err"], iterationsCount=opts["pnp_iters"])
+            assert bool(o["pnp_ok"][s]) == ok
+            if ok:
+                mask = np.zeros(wl2.L, np.uint8)
+                mask[np.flatnonzero(keep)[inl.ravel()]] = 1
+                assert np.array_equal(o["inlier_mask"][s], mask)
+                assert np.array_equal(o["pose"][s], np.concatenate([rv.ravel(), tv.ravel()]))

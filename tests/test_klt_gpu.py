@@ -18,7 +18,12 @@ def _check(p, st, err, rp, rst, rerr, exact_frac=0.5):
     ok = rst.ravel() == 1
     d = np.abs(p - rp)[ok].max(axis=1)
     assert (d <= 0.05).mean() >= 0.99, f"only {(d <= 0.05).mean():.4f} within 0.05 px (max {d.max()})"
-    assert np.abs(err - rerr)[ok].max() < 0.05
+    # err (mean |I - J| over the window, tens of grey levels per pixel of shift on texture) is compared where the
+    # two trackers stopped at the very same position
+    close = np.zeros(len(ok), bool)
+    close[np.flatnonzero(ok)[d == 0]] = True
+    assert close.sum() >= 0.5 * ok.sum()
+    assert np.abs(err - rerr)[close].max() < 0.05
     return d
 
 
@@ -124,3 +129,67 @@ def test_identity_cache_same_results(kitti_pair):
                 assert np.array_equal(a, b)
     finally:
         cv2_compat.set_frame_cache("strict")
+
+
+@pytest.mark.parametrize("shape", ["parking", "malaga"])
+def test_klt_other_dataset_shapes_vs_oracle_and_cv2(shape):
+    """BASELINE configs 2/3 geometry (640x480: 5 pyramid levels, 1024x768: 6) with the reference's own options."""
+    import oracle
+    from monocular_visual_odometry_va4mr_b200 import workload
+    o = workload.REFERENCE_OPTIONS[shape]
+    s = synth.render_sequence(shape, 2, seed=4)
+    f0, f1 = s["frames"]
+    pts = synth.grid_corners(f0, 1000, seed=2)
+    p, st, err = cv2_compat.calcOpticalFlowPyrLK(f0, f1, pts, None, winSize=o["win"], maxLevel=o["max_level"], criteria=o["criteria"])
+    rp, rst, rerr = oracle.calc_optical_flow_pyr_lk(f0, f1, pts, o["win"], o["max_level"], o["criteria"])
+    d = _check(p, st, err, rp, rst, rerr)
+    assert d.max() == 0.0 and np.array_equal(err[rst == 1], rerr[rst == 1])
+    try:
+        import cv2
+    except ImportError:
+        return
+    cp, cst, cerr = cv2.calcOpticalFlowPyrLK(f0, f1, pts, None, winSize=o["win"], maxLevel=o["max_level"], criteria=o["criteria"])
+    _check(p, st, err, cp, cst, cerr)
+
+
+def test_klt_stress_config4_vs_live_cv2(kitti_pair):
+    """BASELINE config 4 tracker part: 20 000 points, 21x21, maxLevel 3 at 1241x376."""
+    cv2 = pytest.importorskip("cv2")
+    import oracle
+    f0, f1 = kitti_pair["frames"]
+    pts = synth.grid_corners(f0, 20000, seed=0)
+    kw = dict(winSize=(21, 21), maxLevel=3, criteria=(3, 30, 0.01))
+    p, st, err = cv2_compat.calcOpticalFlowPyrLK(f0, f1, pts, None, **kw)
+    cp, cst, cerr = cv2.calcOpticalFlowPyrLK(f0, f1, pts, None, **kw)
+    _check(p, st, err, cp, cst, cerr)
+    sub = np.ascontiguousarray(pts[::10])                     # the oracle on every tenth point: bit-equal
+    rp, rst, rerr = oracle.calc_optical_flow_pyr_lk(f0, f1, sub, (21, 21), 3, (3, 30, 0.01))
+    assert np.array_equal(st[::10], rst) and np.array_equal(p[::10][rst.ravel() == 1], rp[rst.ravel() == 1])
+
+
+def test_klt_negative_bilinear_weight(kitti_pair):
+    """iw11 = 2^14 - iw00 - iw01 - iw10 is -1 when the three rounded weights add up to 2^14 + 1 (fractional
+    parts of ~3e-5); cv2 carries the -1 through its signed integer arithmetic.  Regression for the packed
+    16-bit-weight path (the weights must be treated as signed)."""
+    import oracle
+    f0, f1 = kitti_pair["frames"]
+    s = np.float32(16384)
+    one = np.float32(1)
+    pts = []
+    for base in range(30, 340):                       # x == y: both fractional parts are the same tiny value
+        x = np.float32(base)
+        for _ in range(12):
+            x = np.nextafter(x, np.float32(1e9))
+            a = np.float32(x - np.float32(7)) - np.floor(np.float32(x - np.float32(7)))
+            w = 16384 - int(np.rint((one - a) * (one - a) * s)) - 2 * int(np.rint(a * (one - a) * s))
+            if w < 0:
+                pts.append((x, x))
+                break
+    pts = np.ascontiguousarray(np.float32(pts))
+    assert len(pts) >= 50, len(pts)
+    for win, ml in (((15, 15), 0), ((21, 21), 0), ((15, 15), 3)):
+        p, st, err = cv2_compat.calcOpticalFlowPyrLK(f0, f1, pts, None, winSize=win, maxLevel=ml, criteria=(3, 30, 0.01))
+        rp, rst, rerr = oracle.calc_optical_flow_pyr_lk(f0, f1, pts, win, ml, (3, 30, 0.01))
+        assert np.array_equal(st, rst)
+        ok = rst.ravel() == 1
+        assert np.array_equal(p[ok], rp[ok]) and np.array_equal(err[rst == 1], rerr[rst == 1])
