@@ -1,3 +1,5 @@
+"""Per-step wall / device time of the host-buffer batch API in both forms (call by call, prefetch) with the
+in-library stage events -- the probe used to find the copy-engine ordering issue described in DESIGN.md section 6."""
 import time, numpy as np, torch, ctypes as C, sys
 sys.path.insert(0, '.')
 from monocular_visual_odometry_va4mr_b200 import _lib, workload
