@@ -1,0 +1,128 @@
+"""Randomised differential run: CUDA path (through the C ABI) vs the oracle, many shapes / sizes / seeds.
+Not collected by pytest (it runs for minutes); prints every mismatch.
+
+  python tests/fuzz_parity.py [seconds]          (FUZZ_SEED=n for another stream)
+
+Round-1 record: 240 s on a B200 = 632 tracker calls (random image sizes 120..900 x 90..500, six window
+sizes, maxLevel 0..6, all three criteria types, points on quarter-pixel grids and with 3.2e-5 offsets),
+211 goodFeaturesToTrack, 210 knnMatch (with planted duplicate descriptors), 210 solvePnPRansac,
+210 findEssentialMat + recoverPose, 210 min-distance masks: 0 mismatches."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import numpy as np  # noqa: E402
+
+import oracle  # noqa: E402
+from make_golden import make_emat_pair, make_pnp_case, sift_like  # noqa: E402
+from monocular_visual_odometry_va4mr_b200 import cv2_compat, hotpath, synth  # noqa: E402
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+    rng = np.random.default_rng(int(os.environ.get("FUZZ_SEED", "1")))
+    t_end = time.time() + budget
+    stats = dict(klt=0, gftt=0, knn=0, pnp=0, emat=0, rpose=0, mind=0)
+    bad = []
+
+    def rand_frames():
+        shape = str(rng.choice(["kitti", "parking", "malaga"]))
+        w, h = int(rng.integers(120, 900)), int(rng.integers(90, 500))
+        return synth.render_sequence(shape, 2, seed=int(rng.integers(0, 1000)), width=w, height=h, start=int(rng.integers(0, 5)))
+
+    it = 0
+    while time.time() < t_end:
+        it += 1
+        kind = it % 8
+        try:
+            if kind in (0, 1, 2):
+                f0, f1 = rand_frames()["frames"]
+                h, w = f0.shape
+                win = [(15, 15), (21, 21), (9, 13), (31, 31), (5, 7), (21, 15)][int(rng.integers(0, 6))]
+                if w <= win[0] + 2 or h <= win[1] + 2:
+                    continue
+                ml = int(rng.integers(0, 7))
+                crit = (int(rng.choice([1, 2, 3])), int(rng.integers(1, 40)), float(rng.choice([0.01, 0.03, 0.001])))
+                n = int(rng.integers(1, 1500))
+                pts = np.column_stack([rng.uniform(-20, w + 20, n), rng.uniform(-20, h + 20, n)]).astype(np.float32)
+                if rng.random() < 0.5:
+                    pts = np.rint(pts * 4) / 4          # quarter-pixel grid: exact ties in floor / round
+                if rng.random() < 0.3:
+                    pts += np.float32(3.2e-5)           # the negative-weight corner
+                pts = np.ascontiguousarray(pts, np.float32)
+                p, st, err = cv2_compat.calcOpticalFlowPyrLK(f0, f1, pts, None, winSize=win, maxLevel=ml, criteria=crit)
+                rp, rst, rerr = oracle.calc_optical_flow_pyr_lk(f0, f1, pts, win, ml, crit)
+                ok = rst.ravel() == 1
+                if not (np.array_equal(st, rst) and np.array_equal(p[ok], rp[ok]) and np.array_equal(err[rst == 1], rerr[rst == 1])):
+                    bad.append(("klt", (w, h), win, ml, crit, n, int((st != rst).sum()), float(np.abs(p - rp)[ok].max()) if ok.any() else 0))
+                stats["klt"] += 1
+            elif kind == 3:
+                f0 = rand_frames()["frames"][0]
+                mc = int(rng.choice([0, 50, 1400, 5000]))
+                q = float(rng.choice([0.1, 0.03, 0.01, 0.3]))
+                md = float(rng.choice([10, 3, 1, 25, 0, 7.5]))
+                a = cv2_compat.goodFeaturesToTrack(f0, mc, q, md, blockSize=3)
+                b = oracle.good_features_to_track(f0, mc, q, md, 3)
+                if (a is None) != (b is None) or (a is not None and not np.array_equal(a, b)):
+                    bad.append(("gftt", f0.shape, mc, q, md))
+                stats["gftt"] += 1
+            elif kind == 4:
+                nq, nt = int(rng.integers(1, 3000)), int(rng.integers(2, 3000))
+                q, t = sift_like(nq, int(rng.integers(0, 99))), sift_like(nt, int(rng.integers(100, 199)))
+                if rng.random() < 0.5:                  # exact duplicates -> ties (lowest train index first)
+                    t[rng.integers(0, nt, nt // 10)] = q[rng.integers(0, nq, nt // 10)]
+                i1, d1, a1 = cv2_compat.knn2_ratio(q, t, 0.8)
+                i2, d2, a2 = oracle.knn2_ratio(q, t, 0.8)
+                if not (np.array_equal(i1, i2) and np.array_equal(d1, d2) and np.array_equal(a1, a2)):
+                    bad.append(("knn", nq, nt))
+                stats["knn"] += 1
+            elif kind == 5:
+                n, of = int(rng.integers(4, 3000)), float(rng.uniform(0, 0.8))
+                iters, thr = int(rng.choice([100, 500, 2000])), float(rng.choice([8, 5, 2]))
+                obj, img, K = make_pnp_case(n, of, int(rng.integers(0, 10000)))
+                ok, rv, tv, inl = cv2_compat.solvePnPRansac(obj, img, K, np.zeros(4), flags=cv2_compat.SOLVEPNP_P3P, confidence=0.99,
+                                                            reprojectionError=thr, iterationsCount=iters)
+                ro, rrv, rtv, rinl, _ = oracle.solve_pnp_ransac_p3p(obj, img, K, iters, thr, 0.99)
+                same = ok == ro and ((not ok) or np.array_equal(inl, rinl))
+                if same and ok and len(inl) >= 6:       # EPnP on < 6 points is not pinned
+                    same = np.abs(rv - rrv).max() < 1e-6 and np.abs(tv - rtv).max() < 1e-6 * max(1, np.abs(rtv).max())
+                if not same:
+                    bad.append(("pnp", n, of, iters, thr))
+                stats["pnp"] += 1
+            elif kind == 6:
+                n, of = int(rng.integers(5, 3000)), float(rng.uniform(0, 0.6))
+                p1, p2, K = make_emat_pair(n, of, int(rng.integers(0, 10000)))
+                E, m = cv2_compat.findEssentialMat(p1, p2, K, method=cv2_compat.RANSAC, prob=0.99, threshold=1)
+                Eo, mo, _ = oracle.find_essential_mat(p1, p2, K, 0.99, 1.0, 1000)
+                if (E is None) != (Eo is None) or (E is not None and not np.array_equal(m, mo)):
+                    bad.append(("emat", n, of, None if E is None else int((m != mo).sum())))
+                elif E is not None:
+                    g1, R1, t1, k1 = cv2_compat.recoverPose(E, p1, p2, K)
+                    g2, R2, t2, k2 = oracle.recover_pose(E, p1, p2, K)
+                    if g1 != g2 or not np.array_equal(k1, k2) or np.abs(R1 - R2).max() > 1e-12:
+                        bad.append(("rpose", n, of, g1, g2))
+                    stats["rpose"] += 1
+                stats["emat"] += 1
+            else:
+                n, m = int(rng.integers(0, 1500)), int(rng.integers(0, 3000))
+                pts = np.rint(rng.uniform(0, 1200, (n, 2))).astype(np.float32)
+                ex = rng.uniform(0, 1200, (m, 2)).astype(np.float32)
+                if n and m:
+                    k = min(n, m) // 2
+                    ex[:k] = pts[:k] + np.float32([6, 8])          # distance exactly 10
+                if not np.array_equal(hotpath.min_distance_mask(pts, ex, 10.0), oracle.min_distance_mask(pts, ex, 10.0)):
+                    bad.append(("mind", n, m))
+                stats["mind"] += 1
+        except Exception as e:  # noqa: BLE001
+            bad.append(("EXC", kind, repr(e)[:200]))
+    print("runs", stats)
+    print("mismatches", len(bad))
+    for b in bad[:40]:
+        print(b)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
