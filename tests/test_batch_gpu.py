@@ -167,3 +167,38 @@ def test_batch_other_shapes_equal_per_call_path(shape, w, h):
                 mask[np.flatnonzero(keep)[inl.ravel()]] = 1
                 assert np.array_equal(o["inlier_mask"][s], mask)
                 assert np.array_equal(o["pose"][s], np.concatenate([rv.ravel(), tv.ravel()]))
+
+
+def test_batch_ragged_counts(wl):
+    """Sequences with 0, 3, 4, 5 ... landmarks and 0 candidates in one batch: < 4 tracked landmarks -> pnp_ok 0 (the
+    reference raises "Not enough keypoints" there, :360), the others equal the per-call path."""
+    opts = workload.REFERENCE_OPTIONS["kitti"]
+    n_lm = wl.n_lm.copy()
+    n_cand = wl.n_cand.copy()
+    n_lm[:, 0] = 0; n_lm[:, 1] = 3; n_lm[:, 2] = 4; n_lm[:, 3] = 5
+    n_cand[:, 0] = 0; n_cand[:, 4] = 1
+    sb = SequenceBatch(wl.batch, wl.h, wl.w, wl.K, win=opts["win"], max_level=opts["max_level"], criteria=opts["criteria"],
+                       pnp_iters=opts["pnp_iters"], pnp_reproj_err=opts["pnp_err"], pnp_conf=opts["pnp_conf"],
+                       max_landmarks=wl.L, max_candidates=wl.Cn)
+    sb.prime(wl.frames[0])
+    o = sb.step(wl.frames[1], wl.lm_pts[0], wl.lm_obj[0], n_lm[0], wl.cand_pts[0], n_cand[0])
+    for s in range(wl.batch):
+        nl = int(n_lm[0, s])
+        if nl:
+            p, st, _ = cv2_compat.calcOpticalFlowPyrLK(wl.frames[0, s], wl.frames[1, s], wl.lm_pts[0, s, :nl], None,
+                                                       winSize=opts["win"], maxLevel=opts["max_level"], criteria=opts["criteria"])
+            assert np.array_equal(o["lm_status"][s, :nl], st.ravel()) and np.array_equal(o["lm_next"][s, :nl], p)
+            keep = st.ravel() == 1
+        else:
+            keep = np.zeros(0, bool)
+        if keep.sum() < 4:
+            assert o["pnp_ok"][s] == 0 and o["n_inliers"][s] == 0 and not o["inlier_mask"][s].any()
+        else:
+            ok, rv, tv, inl = cv2_compat.solvePnPRansac(wl.lm_obj[0, s, :nl][keep], p[keep], wl.K, np.zeros(4),
+                                                        flags=cv2_compat.SOLVEPNP_P3P, confidence=opts["pnp_conf"],
+                                                        reprojectionError=opts["pnp_err"], iterationsCount=opts["pnp_iters"])
+            assert bool(o["pnp_ok"][s]) == ok
+            if ok:
+                assert int(o["n_inliers"][s]) == len(inl)
+                assert np.array_equal(np.flatnonzero(o["inlier_mask"][s]), np.flatnonzero(keep)[inl.ravel()])
+    sb.close()
