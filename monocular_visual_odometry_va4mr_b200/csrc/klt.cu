@@ -300,6 +300,8 @@ int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab
     else kern = klt_kernel<0, 0>;
     if (smem > 48 * 1024)
         VO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (kern != klt_kernel<0, 0>)   // the staged kernels live in shared memory: let 4 CTAs (64 registers each) fit
+        VO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(a);
     ctx->launches++;
     VO_CUDA(ctx, cudaGetLastError());

@@ -118,7 +118,7 @@ __device__ __forceinline__ void interp_run8(const uint8_t* img, int off, int sh8
 }
 
 template <int WW, int WH>
-__global__ void __launch_bounds__(KLT_WARPS * 32)
+__global__ void __launch_bounds__(KLT_WARPS * 32, 4)
 klt_kernel_v2(const KltArgs a)
 {
     using C = KV2<WW, WH>;
