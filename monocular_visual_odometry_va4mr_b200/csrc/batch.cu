@@ -149,7 +149,11 @@ extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batc
     if (!rc) rc = vo_rng_table(ctx, B->n_raw, &B->rng);
     if (rc) { b200vo_batch_destroy(B); return rc; }
     cudaStreamCreateWithFlags(&B->pre_stream, cudaStreamNonBlocking);
-    for (auto& st : B->chunk_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    {   // chunk streams carry pyramids + the landmark tracker: ahead of the candidate tracker on the ctx stream
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        for (auto& st : B->chunk_stream) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest);
+    }
     for (auto& e : B->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto& e : B->copy_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&B->done_ev, cudaEventDisableTiming);
@@ -519,7 +523,7 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     } else {
         // The frames go up chunk by chunk, back to back on the copy stream; chunk k's pyramids + landmark tracker
         // run on a compute stream as soon as its frames have landed (the later chunks are on the wire meanwhile);
-        // then the candidate tracker for the whole batch on the ctx stream with the pose chain beside it.
+        // its candidate tracker follows on the ctx stream, and the pose chain starts when the last landmark tracks are in.
         int rc_chunks = 0;
         if (nchunks > 1) {
             VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->step_end_ev, 0));   // B->raw is free again
@@ -545,22 +549,32 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
             ctx->stream = main_stream;
             if (!rc_chunks && nchunks > 1) {
                 VO_CUDA(ctx, cudaEventRecord(B->chunk_ev[k], cs));
+                // this chunk's candidates follow on the (normal-priority) ctx stream: they fill the SMs whenever the
+                // landmark trackers of later chunks are still waiting for their frames
                 VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->chunk_ev[k], 0));
+                VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->chunk_ev[k], 0));
+                rc_chunks = batch_track(B, b0, n_here, nullptr, (const float*)(di + o_lmp), (const int*)(di + o_nlm),
+                                        (const float*)(di + o_cp), (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms,
+                                        (float*)(dq + q_cn), dq + q_cs, 2);
             }
         }
         if (rc_chunks) return rc_chunks;
-        VO_CUDA(ctx, cudaEventRecord(B->lm_ev, main_stream));      // every chunk's pyramids and landmark tracks are done
-        VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->lm_ev, 0));
+        if (nchunks == 1) {
+            VO_CUDA(ctx, cudaEventRecord(B->lm_ev, main_stream));
+            VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->lm_ev, 0));
+            VO_TRY(batch_track(B, 0, nb, nullptr, (const float*)(di + o_lmp), (const int*)(di + o_nlm), (const float*)(di + o_cp),
+                               (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms, (float*)(dq + q_cn), dq + q_cs, 2));
+        }
+        VO_CUDA(ctx, cudaEventRecord(B->cand_ev, main_stream));
+        // the pose chain (high priority) starts once every chunk's landmark tracks are done
         VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->obj_ev, 0));
+        VO_CUDA(ctx, cudaEventRecord(B->lm_ev, B->pose_stream));
         ctx->stream = B->pose_stream;
         const int rc_pose = batch_pose(B, (const float*)(di + o_lmo), (const int*)(di + o_nlm), (const float*)(dq + q_lmn), dq + q_lms,
                                        (double*)(dq + q_pose), dq + q_ok, dq + q_mask, (int*)(dq + q_ni));
         ctx->stream = main_stream;
         if (rc_pose) return rc_pose;
         VO_CUDA(ctx, cudaEventRecord(B->pose_ev, B->pose_stream));
-        VO_TRY(batch_track(B, 0, nb, nullptr, (const float*)(di + o_lmp), (const int*)(di + o_nlm), (const float*)(di + o_cp),
-                           (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms, (float*)(dq + q_cn), dq + q_cs, 2));
-        VO_CUDA(ctx, cudaEventRecord(B->cand_ev, main_stream));
         VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->pose_ev, 0));
     }
     VO_TRY(batch_finish(B));
