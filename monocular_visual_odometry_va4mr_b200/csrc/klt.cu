@@ -294,8 +294,7 @@ int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab
     const long long total_warps = (long long)batch * (a.cap[0] + a.cap[1]);
     const unsigned grid = (unsigned)((total_warps + KLT_WARPS - 1) / KLT_WARPS);
     void (*kern)(const KltArgs) = nullptr;
-    if (getenv("B200VO_KLT_V1")) kern = klt_kernel<0, 0>;
-    else if (kp.win_w == 21 && kp.win_h == 21) { kern = klt_kernel_v2<21, 21>; smem = (size_t)KV2<21, 21>::PER_WARP * KLT_WARPS + 64; }
+    if (kp.win_w == 21 && kp.win_h == 21) { kern = klt_kernel_v2<21, 21>; smem = (size_t)KV2<21, 21>::PER_WARP * KLT_WARPS + 64; }
     else if (kp.win_w == 15 && kp.win_h == 15) { kern = klt_kernel_v2<15, 15>; smem = (size_t)KV2<15, 15>::PER_WARP * KLT_WARPS + 64; }
     else kern = klt_kernel<0, 0>;
     if (smem > 48 * 1024)
