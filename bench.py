@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences per step in the bounded CPU sample (0 = one per host core, at least 4)")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="skip the extra one-sequence-per-call measurement")
     return ap.parse_args()
 
 
@@ -373,6 +374,48 @@ def main():
                                       "pnp_beside_klt_candidates": float(stage_ms[2]) / max(int(nprof[0]), 1)},
                 "note": "klt_kernel_v2 is instruction-issue bound (smsp issue active 78 %, profiles/r1k_klt_kernel_full.txt): integer bilinear taps from shared-memory-staged windows; DRAM traffic ~ the algorithmic bytes; see DESIGN.md"}
 
+    # ---- extra (not the headline): ONE sequence per call -- BASELINE config 0's shape, latency-bound ----
+    single = None
+    if rank == 0 and world == 1 and not args.no_single:
+        wl1 = workload.TrackWorkload(args.shape, batch=1, n_frames=args.frames, n_landmarks=args.landmarks, n_candidates=args.candidates,
+                                     n_distinct=1, seed=sharding.sequence_seed(0), cap_landmarks=capL, cap_candidates=capC)
+        sb1 = SequenceBatch(1, wl1.h, wl1.w, wl1.K, win=opts["win"], max_level=opts["max_level"], criteria=opts["criteria"],
+                            pnp_iters=opts["pnp_iters"], pnp_reproj_err=opts["pnp_err"], pnp_conf=opts["pnp_conf"],
+                            max_landmarks=wl1.L, max_candidates=wl1.Cn, ctx=ctx)
+        f1 = sb1.pinned_frames(wl1.F)
+        f1[:] = wl1.frames
+        a1 = [sb1.pinned_like(x) for x in (wl1.lm_pts, wl1.lm_obj, wl1.n_lm, wl1.cand_pts, wl1.n_cand)]
+        n1 = min(K, 200)
+        o1 = workload.frame_order(wl1.F, n1 + W + 1)
+        sb1.prime(f1[o1[0]])
+        sb1.submit_frames(f1[o1[1]])
+        for t in range(W + n1):
+            if t == W:
+                ctx.sync()
+                t0 = time.perf_counter()
+            sb1.submit_frames(f1[o1[t + 2]])
+            sb1.step(None, a1[0][o1[t]], a1[1][o1[t]], a1[2][o1[t]], a1[3][o1[t]], a1[4][o1[t]])
+        dt1 = time.perf_counter() - t0
+        sb1.step(None, a1[0][0], a1[1][0], a1[2][0], a1[3][0], a1[4][0])
+        single = {"value": n1 / dt1, "unit": "frames/s", "ms_per_frame": 1e3 * dt1 / n1,
+                  "what": "one sequence per b200vo_batch_step call (batch = 1), host buffers in and out, next frame prefetched: "
+                          "the latency-bound shape of BASELINE config 0; a single sequence cannot be sharded (frame i needs frame i-1)"}
+        if not args.no_cpu_baseline:
+            try:
+                import cv2
+                cv2.setNumThreads(os.cpu_count() or 1)
+                nc1 = 30
+                for t in range(3):
+                    cpu_reference_step(cv2, wl1, opts, o1[t], o1[t + 1], [0])
+                t0 = time.perf_counter()
+                for t in range(3, 3 + nc1):
+                    cpu_reference_step(cv2, wl1, opts, o1[t], o1[t + 1], [0])
+                single["cv2_value"] = nc1 / (time.perf_counter() - t0)
+                single["cv2_what"] = f"cv2 {cv2.__version__}, same calls, one sequence, cv2-internal threading on {os.cpu_count()} cores"
+            except ImportError:
+                pass
+        sb1.close()
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -393,6 +436,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "single_sequence": single,
         }
         print(json.dumps(line))
     sb.close()

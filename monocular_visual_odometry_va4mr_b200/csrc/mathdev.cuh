@@ -97,19 +97,26 @@ template <int N>
 __device__ inline void jacobi_svd(const double* A, double* W, double* U, double* Vt, double* At)
 {
     const double eps = DBL_EPSILON * 10;
+#pragma unroll
     for (int i = 0; i < N; ++i) {
         double sd = 0;
+#pragma unroll
         for (int k = 0; k < N; ++k) { At[i * N + k] = A[k * N + i]; sd += At[i * N + k] * At[i * N + k]; }
         W[i] = sd;
+#pragma unroll
         for (int k = 0; k < N; ++k) Vt[i * N + k] = (i == k) ? 1.0 : 0.0;
     }
+#pragma unroll 1
     for (int iter = 0; iter < 30; ++iter) {
         bool changed = false;
+#pragma unroll
         for (int i = 0; i < N - 1; ++i)
+#pragma unroll
             for (int j = i + 1; j < N; ++j) {
                 double* Ai = At + i * N;
                 double* Aj = At + j * N;
                 double a = W[i], p = 0, b = W[j];
+#pragma unroll
                 for (int k = 0; k < N; ++k) p += Ai[k] * Aj[k];
                 if (fabs(p) <= eps * sqrt(a * b)) continue;
                 p *= 2;
@@ -124,6 +131,7 @@ __device__ inline void jacobi_svd(const double* A, double* W, double* U, double*
                     s = p / (gamma * c * 2);
                 }
                 a = b = 0;
+#pragma unroll
                 for (int k = 0; k < N; ++k) {
                     const double t0 = c * Ai[k] + s * Aj[k];
                     const double t1 = -s * Ai[k] + c * Aj[k];
@@ -134,6 +142,7 @@ __device__ inline void jacobi_svd(const double* A, double* W, double* U, double*
                 changed = true;
                 double* Vi = Vt + i * N;
                 double* Vj = Vt + j * N;
+#pragma unroll
                 for (int k = 0; k < N; ++k) {
                     const double t0 = c * Vi[k] + s * Vj[k];
                     const double t1 = -s * Vi[k] + c * Vj[k];
@@ -142,22 +151,30 @@ __device__ inline void jacobi_svd(const double* A, double* W, double* U, double*
             }
         if (!changed) break;
     }
+#pragma unroll
     for (int i = 0; i < N; ++i) {
         double sd = 0;
+#pragma unroll
         for (int k = 0; k < N; ++k) sd += At[i * N + k] * At[i * N + k];
         W[i] = sqrt(sd);
     }
+#pragma unroll
     for (int i = 0; i < N - 1; ++i) {
         int j = i;
+#pragma unroll
         for (int k = i + 1; k < N; ++k) if (W[j] < W[k]) j = k;
         if (i != j) {
             double tw = W[i]; W[i] = W[j]; W[j] = tw;
+#pragma unroll
             for (int k = 0; k < N; ++k) { double tt = At[i * N + k]; At[i * N + k] = At[j * N + k]; At[j * N + k] = tt; }
+#pragma unroll
             for (int k = 0; k < N; ++k) { double tt = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = tt; }
         }
     }
+#pragma unroll
     for (int i = 0; i < N; ++i) {
         const double sc = W[i] > DBL_MIN ? 1 / W[i] : 0.;
+#pragma unroll
         for (int k = 0; k < N; ++k) U[k * N + i] = At[i * N + k] * sc;
     }
 }
@@ -168,33 +185,46 @@ __device__ inline void qr_lstsq6(const double* Ain, const double* bin, double* x
 {
     constexpr int M = 6;
     double A[M * NC], b[M];
+#pragma unroll
     for (int i = 0; i < M * NC; ++i) A[i] = Ain[i];
+#pragma unroll
     for (int i = 0; i < M; ++i) b[i] = bin[i];
+#pragma unroll
     for (int k = 0; k < NC; ++k) {
         double nrm = 0;
+#pragma unroll
         for (int i = k; i < M; ++i) nrm += A[i * NC + k] * A[i * NC + k];
         nrm = sqrt(nrm);
         if (nrm == 0) continue;
         const double alpha = A[k * NC + k] > 0 ? -nrm : nrm;
         double v[M];
+#pragma unroll
         for (int i = k; i < M; ++i) v[i] = A[i * NC + k];
         v[k] -= alpha;
         double vn = 0;
+#pragma unroll
         for (int i = k; i < M; ++i) vn += v[i] * v[i];
         if (vn == 0) continue;
+#pragma unroll
         for (int j = k; j < NC; ++j) {
             double s = 0;
+#pragma unroll
             for (int i = k; i < M; ++i) s += v[i] * A[i * NC + j];
             s = 2 * s / vn;
+#pragma unroll
             for (int i = k; i < M; ++i) A[i * NC + j] -= s * v[i];
         }
         double s = 0;
+#pragma unroll
         for (int i = k; i < M; ++i) s += v[i] * b[i];
         s = 2 * s / vn;
+#pragma unroll
         for (int i = k; i < M; ++i) b[i] -= s * v[i];
     }
+#pragma unroll
     for (int k = NC - 1; k >= 0; --k) {
         double s = b[k];
+#pragma unroll
         for (int j = k + 1; j < NC; ++j) s -= A[k * NC + j] * x[j];
         x[k] = A[k * NC + k] != 0 ? s / A[k * NC + k] : 0;
     }

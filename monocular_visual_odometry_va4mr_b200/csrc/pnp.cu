@@ -250,9 +250,32 @@ pnp_select_kernel(PnpArgs a)
 // A (in/out, destroyed) and V (out, eigenvectors in columns) live in shared memory, row-major 12x12.
 // Only used for EPnP's M^T M, where the result is independent of eigenvector signs and of the
 // rotation order (unlike the 3x3 control-point SVD, which replays OpenCV's order exactly).
-__device__ inline void warp_jacobi_eig12(double* A, double* V, double* cs /* [12] */, int lane)
+__device__ inline void warp_jacobi_eig12(double* A, double* V, double* cs /* [12] + pair table */, int lane)
 {
+    // pair table of the tournament: pq[rnd][pr] = p | q << 8 (p < q), built once
+    unsigned short* pq = reinterpret_cast<unsigned short*>(cs + 12);
+    for (int k = lane; k < 66; k += 32) {
+        const int rnd = k / 6, pr = k - rnd * 6;
+        int p = pr == 0 ? 11 : (rnd + pr) % 11;
+        int q = (rnd + 11 - pr) % 11;
+        if (p > q) { const int t = p; p = q; q = t; }
+        pq[k] = (unsigned short)(p | (q << 8));
+    }
     for (int k = lane; k < 144; k += 32) V[k] = (k / 12 == k % 12) ? 1.0 : 0.0;
+    // this lane's fixed element slots: columns pass (A and V: 12 rows x 6 pairs x 2 matrices = 144), rows pass (12 x 6 = 72)
+    int c_row[5], c_pr[5], r_k[3], r_pr[3];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int e = lane + 32 * i, m = e / 72, r = (e % 72) / 6;
+        c_pr[i] = e % 6;
+        c_row[i] = e < 144 ? m * 144 + r * 12 : -1;       // V follows A in shared memory (A + 144)
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int e = lane + 32 * i;
+        r_pr[i] = e % 6;
+        r_k[i] = e < 72 ? e / 6 : -1;
+    }
     __syncwarp();
     for (int sweep = 0; sweep < 30; ++sweep) {
         // convergence: sum of squared off-diagonal entries relative to the diagonal
@@ -265,11 +288,8 @@ __device__ inline void warp_jacobi_eig12(double* A, double* V, double* cs /* [12
         for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dia += __shfl_xor_sync(0xffffffffu, dia, o); }
         if (off <= 1e-30 * dia || off == 0) break;
         for (int rnd = 0; rnd < 11; ++rnd) {
-            // tournament pairing: player 11 fixed, the others rotate
             if (lane < 6) {
-                int p = lane == 0 ? 11 : (rnd + lane) % 11;
-                int q = (rnd + 11 - lane) % 11;
-                if (p > q) { const int t = p; p = q; q = t; }
+                const int pqv = pq[rnd * 6 + lane], p = pqv & 0xff, q = pqv >> 8;
                 const double apq = A[p * 12 + q];
                 double c = 1.0, sn = 0.0;
                 if (fabs(apq) > 1e-300) {
@@ -280,29 +300,29 @@ __device__ inline void warp_jacobi_eig12(double* A, double* V, double* cs /* [12
                 cs[2 * lane] = c; cs[2 * lane + 1] = sn;
             }
             __syncwarp();
-            // columns p,q of A and of V: 12 rows x 6 pairs, two matrices
-            for (int e = lane; e < 144; e += 32) {
-                const int m = e / 72, r = (e % 72) / 6, pr = e % 6;
-                int p = pr == 0 ? 11 : (rnd + pr) % 11;
-                int q = (rnd + 11 - pr) % 11;
-                if (p > q) { const int t = p; p = q; q = t; }
-                const double c = cs[2 * pr], sn = cs[2 * pr + 1];
-                double* M = m ? V : A;
-                const double x = M[r * 12 + p], y = M[r * 12 + q];
-                M[r * 12 + p] = c * x - sn * y;
-                M[r * 12 + q] = sn * x + c * y;
+            // columns p,q of A and of V
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (c_row[i] >= 0) {
+                    const int pqv = pq[rnd * 6 + c_pr[i]], p = pqv & 0xff, q = pqv >> 8;
+                    const double c = cs[2 * c_pr[i]], sn = cs[2 * c_pr[i] + 1];
+                    double* M = A + c_row[i];
+                    const double x = M[p], y = M[q];
+                    M[p] = c * x - sn * y;
+                    M[q] = sn * x + c * y;
+                }
             }
             __syncwarp();
             // rows p,q of A
-            for (int e = lane; e < 72; e += 32) {
-                const int k = e / 6, pr = e % 6;
-                int p = pr == 0 ? 11 : (rnd + pr) % 11;
-                int q = (rnd + 11 - pr) % 11;
-                if (p > q) { const int t = p; p = q; q = t; }
-                const double c = cs[2 * pr], sn = cs[2 * pr + 1];
-                const double x = A[p * 12 + k], y = A[q * 12 + k];
-                A[p * 12 + k] = c * x - sn * y;
-                A[q * 12 + k] = sn * x + c * y;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (r_k[i] >= 0) {
+                    const int pqv = pq[rnd * 6 + r_pr[i]], p = pqv & 0xff, q = pqv >> 8;
+                    const double c = cs[2 * r_pr[i]], sn = cs[2 * r_pr[i] + 1];
+                    const double x = A[p * 12 + r_k[i]], y = A[q * 12 + r_k[i]];
+                    A[p * 12 + r_k[i]] = c * x - sn * y;
+                    A[q * 12 + r_k[i]] = sn * x + c * y;
+                }
             }
             __syncwarp();
         }
@@ -380,8 +400,10 @@ __device__ inline void epnp_pose_from_betas(EpnpShared& S, const double* betas, 
 
 __device__ inline void epnp_gauss_newton(const double* L, const double* rho, double* b)
 {
+#pragma unroll 1
     for (int it = 0; it < 5; ++it) {
         double A[24], B[6], x[4];
+#pragma unroll
         for (int i = 0; i < 6; ++i) {
             const double* r = L + 10 * i;
             A[4 * i + 0] = 2 * r[0] * b[0] + r[1] * b[1] + r[3] * b[2] + r[6] * b[3];
@@ -393,6 +415,7 @@ __device__ inline void epnp_gauss_newton(const double* L, const double* rho, dou
                              r[8] * b[2] * b[3] + r[9] * b[3] * b[3]);
         }
         qr_lstsq6<4>(A, B, x);
+#pragma unroll
         for (int k = 0; k < 4; ++k) b[k] += x[k];
     }
 }
