@@ -99,3 +99,23 @@ def run_on_trace(ops):
     for i in range(b1 + 1, len(frames)):
         vo.step(frames[i])
     return g, vo
+
+
+def run_long(ops):
+    """The 26-frame run of tests/golden/reference_long.npz (made by make_reference_long.py): only the bootstrap
+    matches, the inlier counts and the poses of the reference are stored; frames are re-rendered."""
+    import os
+    import zlib
+
+    from conftest import GOLDEN
+    from monocular_visual_odometry_va4mr_b200 import synth
+    g = np.load(os.path.join(GOLDEN, "reference_long.npz"))
+    frames = synth.render_sequence(str(g["render_shape"]), int(g["render_n"]), seed=int(g["render_seed"]))["frames"]
+    assert np.array_equal(np.array([zlib.crc32(f.tobytes()) for f in frames], np.uint32), g["frame_crc"]), "renderer drifted"
+    vo = MiniVO(g["K"], REFERENCE_KITTI_OPTIONS, ops)
+    b0, b1 = (int(v) for v in g["bootstrap"])
+    vo.initialize(g["p1"], g["p2"], frames[b1])
+    for i in range(b1 + 1, len(frames)):
+        vo.step(frames[i])
+    poses = np.array([np.hstack([np.reshape(R, 9), np.reshape(t, 3)]) for R, t in vo.transforms], np.float64)
+    return g, vo, poses

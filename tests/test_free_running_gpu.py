@@ -8,13 +8,13 @@ from types import SimpleNamespace
 import numpy as np
 import pytest
 
-from mini_vo import run_on_trace
+from mini_vo import run_long, run_on_trace
 from monocular_visual_odometry_va4mr_b200 import cv2_compat, hotpath
 
 pytestmark = pytest.mark.gpu
 
 
-def test_free_running_pipeline_on_cuda_path():
+def _cuda_ops():
     def klt(prev, nxt, pts, win, ml, crit):
         p, st, _ = cv2_compat.calcOpticalFlowPyrLK(prev, nxt, pts, None, winSize=win, maxLevel=ml, criteria=crit)
         return p, st
@@ -29,6 +29,61 @@ def test_free_running_pipeline_on_cuda_path():
                                                                                     confidence=conf, reprojectionError=err, iterationsCount=it),
         triangulate=lambda K, o, first, keys, tr, transforms, R, t: hotpath.triangulate_landmarks(K, o, first, keys, tr, transforms, R, t),
         min_distance=hotpath.min_distance_mask)
+    return ops
+
+
+def test_free_running_26_frames_on_cuda_path():
+    """completes without ValueError; over the first 10 frames the camera positions stay within
+    0.5 % of the path length of the reference's; over the whole run within the reference's own sensitivity
+    envelope (+-0.01 px tracker noise moves the reference itself by 2.5-10 % of the path length)."""
+    g, vo, poses = run_long(_cuda_ops())
+    ref = g["poses"]
+    assert poses.shape == ref.shape and len(vo.num_pts) == len(g["num_pts"])
+    path = np.concatenate([[0.0], np.cumsum(np.linalg.norm(np.diff(ref[:, 9:], axis=0), axis=1))])
+    dev = np.linalg.norm(poses[:, 9:] - ref[:, 9:], axis=1)
+    assert np.all(dev[:11] <= 0.005 * np.maximum(path[:11], 1.0)), dev[:11]
+    assert np.sqrt((dev ** 2).mean()) <= 0.10 * path[-1], (dev.max(), path[-1])
+    same = sum(int(a == b) for a, b in zip(vo.num_pts, g["num_pts"]))
+    print("26-frame free run: identical inlier counts in", same, "of", len(vo.num_pts), "frames; max position deviation",
+          float(dev.max()), "of path", float(path[-1]), "max rotation deviation", float(np.abs(poses[:, :9] - ref[:, :9]).max()))
+
+
+def _oracle_ops():
+    import oracle
+
+    def klt(prev, nxt, pts, win, ml, crit):
+        p, st, _ = oracle.calc_optical_flow_pyr_lk(prev, nxt, pts, win, ml, crit)
+        return p, st
+
+    def emat(p1, p2, K, prob, thr):
+        E, m, _ = oracle.find_essential_mat(p1, p2, K, prob, thr, 1000)
+        return E, m
+
+    def pnp(obj, img, K, it, err, conf):
+        ok, rv, tv, inl, _ = oracle.solve_pnp_ransac_p3p(obj, img, K, it, err, conf)
+        return ok, rv, tv, inl
+
+    def tri(K, o, first, keys, tr, transforms, R, t):
+        return oracle.triangulate_landmarks(K, (o['min_dist_landmarks'], o['max_dist_landmarks'], o['min_baseline_angle'], o['min_baseline_frames']),
+                                            first, keys, tr, oracle.pack_poses(transforms), np.hstack([np.reshape(R, 9), np.reshape(t, 3)]))
+
+    return SimpleNamespace(klt=klt, gftt=lambda img, mc, q, md, bs: oracle.good_features_to_track(img, mc, q, md, bs), findEssentialMat=emat,
+                           recoverPose=lambda E, p1, p2, K: oracle.recover_pose(E, p1, p2, K), solvePnPRansac=pnp, triangulate=tri,
+                           min_distance=oracle.min_distance_mask)
+
+
+def test_free_running_cuda_equals_free_running_oracle():
+    """Where the 26-frame CUDA run leaves the reference's trajectory it does so because of the tracker's documented
+    <= 0.02 px differences from cv2 (exact integer sums vs float32 SIMD lanes), not because of the CUDA code: the same
+    loop driven by the ORACLE alone gives the CUDA run's inlier counts and poses."""
+    g, vo_c, poses_c = run_long(_cuda_ops())
+    _, vo_o, poses_o = run_long(_oracle_ops())
+    assert vo_c.num_pts == vo_o.num_pts
+    assert np.abs(poses_c - poses_o).max() < 1e-6
+
+
+def test_free_running_pipeline_on_cuda_path():
+    ops = _cuda_ops()
     g, vo = run_on_trace(ops)
     ref = [int(v) for v in g["num_pts"]]
     n = sum(1 for k in g.files if k.startswith("tri") and k.endswith("_cur"))

@@ -7,10 +7,10 @@ import numpy as np
 import pytest
 
 import oracle
-from mini_vo import run_on_trace
+from mini_vo import run_long, run_on_trace
 
 
-def test_driver_reproduces_reference_run_with_cv2():
+def _cv2_ops():
     cv2 = pytest.importorskip("cv2")
 
     def klt(prev, nxt, pts, win, ml, crit):
@@ -30,6 +30,17 @@ def test_driver_reproduces_reference_run_with_cv2():
         solvePnPRansac=lambda obj, img, K, it, err, conf: cv2.solvePnPRansac(obj, img, K, np.zeros(4), flags=cv2.SOLVEPNP_P3P, confidence=conf,
                                                                              reprojectionError=err, iterationsCount=it),
         triangulate=tri, min_distance=oracle.min_distance_mask)
+    return ops
+
+
+def test_driver_reproduces_long_reference_run_with_cv2():
+    g, vo, poses = run_long(_cv2_ops())
+    assert vo.num_pts == [int(v) for v in g["num_pts"]]
+    assert poses.shape == g["poses"].shape and np.abs(poses - g["poses"]).max() < 1e-8
+
+
+def test_driver_reproduces_reference_run_with_cv2():
+    ops = _cv2_ops()
     g, vo = run_on_trace(ops)
     assert vo.num_pts == [int(v) for v in g["num_pts"]]
     n = sum(1 for k in g.files if k.startswith("tri") and k.endswith("_cur"))
