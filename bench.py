@@ -374,6 +374,35 @@ def main():
                                       "pnp_beside_klt_candidates": float(stage_ms[2]) / max(int(nprof[0]), 1)},
                 "note": "klt_kernel_v2 is instruction-issue bound (smsp issue active 78 %, profiles/r1k_klt_kernel_full.txt): integer bilinear taps from shared-memory-staged windows; DRAM traffic ~ the algorithmic bytes; see DESIGN.md"}
 
+    # ---- extra (not the headline): Shi-Tomasi detection (reference :256, feature_adding runs it every frame) for the
+    # whole batch on the resident frames ----
+    detect = None
+    if rank == 0 and world == 1 and not args.no_single:
+        sb.good_features(1400, 0.1, 10.0)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            sb.good_features(1400, 0.1, 10.0)
+        dt = (time.perf_counter() - t0) / 20
+        detect = {"ms_per_step": 1e3 * dt, "frames_per_s": wl.batch / dt,
+                  "what": f"b200vo_batch_good_features(1400, 0.1, 10) on the {wl.batch} resident frames, corner lists read back to the host"}
+        if not args.no_cpu_baseline:
+            try:
+                import cv2
+                from concurrent.futures import ThreadPoolExecutor
+                cores = os.cpu_count() or 1
+                cv2.setNumThreads(1)
+                imgs = [wl.frames[0, s_ % wl.batch] for s_ in range(cores)]
+                with ThreadPoolExecutor(max_workers=cores) as pool:
+                    list(pool.map(lambda im: cv2.goodFeaturesToTrack(im, 1400, 0.1, 10, blockSize=3), imgs))
+                    t0 = time.perf_counter()
+                    for _ in range(5):
+                        list(pool.map(lambda im: cv2.goodFeaturesToTrack(im, 1400, 0.1, 10, blockSize=3), imgs))
+                    detect["cv2_frames_per_s"] = 5 * len(imgs) / (time.perf_counter() - t0)
+                cv2.setNumThreads(cores)
+                detect["cv2_what"] = f"cv2.goodFeaturesToTrack, one thread per image on {cores} cores"
+            except ImportError:
+                pass
+
     # ---- extra (not the headline): ONE sequence per call -- BASELINE config 0's shape, latency-bound ----
     single = None
     if rank == 0 and world == 1 and not args.no_single:
@@ -437,6 +466,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "single_sequence": single,
+            "detect": detect,
         }
         print(json.dumps(line))
     sb.close()

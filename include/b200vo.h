@@ -209,6 +209,15 @@ int b200vo_batch_step_dev(b200vo_batch* b, const uint8_t* frames_dev, const floa
                           uint8_t* lm_status_dev, float* cand_next_dev, uint8_t* cand_status_dev,
                           double* pose_dev, uint8_t* pnp_ok_dev, uint8_t* inlier_mask_dev,
                           int32_t* n_inliers_dev);
+/*
+ * cv2.goodFeaturesToTrack (:256) on the CURRENT frame of every sequence of the batch (the frames the last
+ * prime / step made resident): no upload, one set of launches, one read-back.  corners float32
+ * (batch, max_corners, 2) in cv2's order, n_corners int32 (batch).  blockSize 3, no mask, no Harris;
+ * needs min_dist >= 1 and max_corners > 0 (what the reference passes); more than 32768 candidates above
+ * the quality threshold in one image -> B200VO_E_UNSUPPORTED (use b200vo_good_features_to_track).
+ */
+int b200vo_batch_good_features(b200vo_batch* b, int max_corners, double quality, double min_dist,
+                               float* corners, int32_t* n_corners);
 /* Per-stage device timing of batch steps (CUDA events on the ctx stream).  Stages:
  * 0 = pyramid build, 1 = KLT kernel, 2 = compaction + PnP-RANSAC + EPnP + mask scatter. */
 #define B200VO_PROF_STAGES 3

@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200vo_batch_destroy": (None, [C.c_void_p]),
     "b200vo_batch_prime": (C.c_int, [C.c_void_p, c_u8p]),
     "b200vo_batch_submit_frames": (C.c_int, [C.c_void_p, c_u8p]),
+    "b200vo_batch_good_features": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, c_f32p, c_i32p]),
     "b200vo_batch_step": (C.c_int, [
         C.c_void_p, c_u8p, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p, c_f32p, c_u8p, c_f32p, c_u8p,
         c_f64p, c_u8p, c_u8p, c_i32p]),

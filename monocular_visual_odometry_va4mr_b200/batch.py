@@ -132,6 +132,16 @@ class SequenceBatch:
                     cand_status=self.cand_status, pose=self.pose, pnp_ok=self.pnp_ok,
                     inlier_mask=self.inlier_mask, n_inliers=self.n_inliers)
 
+    def good_features(self, max_corners=1400, quality=0.1, min_dist=10.0):
+        """cv2.goodFeaturesToTrack (reference :256) on the current frame of every sequence (the frames the last
+        prime()/step() left resident).  -> (corners float32 (batch, max_corners, 2), n int32 (batch,)); row s holds
+        n[s] corners in cv2's order."""
+        corners = np.zeros((self.batch, int(max_corners), 2), np.float32)
+        n = np.zeros(self.batch, np.int32)
+        self._chk(self.ctx.lib.b200vo_batch_good_features(self.h, int(max_corners), float(quality), float(min_dist),
+                                                          _p(corners, c_f32p), _p(n, c_i32p)), "b200vo_batch_good_features")
+        return corners, n
+
     def step_dev(self, frames_dev, lm_pts_dev, lm_obj_dev, n_lm_dev, cand_pts_dev, n_cand_dev, out_dev: dict):
         """Device pointers in/out (ints from tensor.data_ptr()); asynchronous on the ctx stream."""
         o = out_dev

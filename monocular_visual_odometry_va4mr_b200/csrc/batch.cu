@@ -32,6 +32,7 @@ struct b200vo_batch {
     DevBuf pts_in;           // host-input path: lm_pts | lm_obj | n_lm | cand_pts | n_cand
     DevBuf outs;             // host-input path: outputs
     DevBuf work;             // compacted landmarks + PnP workspace
+    DevBuf gftt_ws;          // batched corner detection workspace
     // carved from `work`
     float* c_obj; float* c_img; int* c_n; int* c_orig; int* inliers; uint8_t* c_mask;
     void* pnp_ws;
@@ -189,7 +190,7 @@ extern "C" void b200vo_batch_destroy(b200vo_batch* B)
         for (auto& e : B->q_ev) cudaEventDestroy(e);
         cudaEventDestroy(B->step_end_ev);
     }
-    for (DevBuf* d : {&B->raw, &B->raw_pre, &B->pts_in, &B->outs, &B->work}) if (d->p) cudaFree(d->p);
+    for (DevBuf* d : {&B->raw, &B->raw_pre, &B->pts_in, &B->outs, &B->work, &B->gftt_ws}) if (d->p) cudaFree(d->p);
     if (B->prof_init) for (auto& row : B->prof_ev) for (auto& e : row) cudaEventDestroy(e);
     if (B->chunk_stream[0]) {
         for (auto& st : B->chunk_stream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -602,6 +603,44 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     for (auto& o : outs)
         if (o.dst && o.bytes && o.staged) memcpy(o.dst, ho + o.off, o.bytes);
+    return 0;
+}
+
+// cv2.goodFeaturesToTrack (reference :256) on the CURRENT frame of every sequence -- the frames whose pyramids
+// the last prime / step left resident -- in one set of launches; no upload, one read-back.
+extern "C" int b200vo_batch_good_features(b200vo_batch* B, int max_corners, double quality, double min_dist,
+                                          float* corners, int32_t* n_corners)
+{
+    if (!B || !corners || !n_corners) return B200VO_E_BADARG;
+    b200vo_ctx* ctx = B->ctx;
+    if (!B->primed) return vo_set_err(ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const b200vo_batch_cfg& c = B->cfg;
+    const int nb = B->batch;
+    if (max_corners <= 0) return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "batched detection needs maxCorners > 0");
+    VO_TRY(vo_reserve(ctx, B->gftt_ws, vo_gftt_batch_workspace(c.rows, c.cols, nb, max_corners)));
+    float* d_out = nullptr;
+    int* d_small = nullptr;
+    VO_TRY(vo_gftt_batch_launch(ctx, (const uint8_t*)B->slabs[B->cur].p + B->geom.off[0], B->geom.slab_bytes, B->geom.pitch[0], c.rows, c.cols,
+                                nb, max_corners, quality, min_dist, B->gftt_ws.p, &d_out, &d_small));
+    const size_t b_out = vo_align((size_t)max_corners * 8, 256);
+    const size_t out_bytes = b_out * nb, small_bytes = (size_t)nb * VO_GFTT_SMALL * sizeof(int);
+    VO_TRY(vo_reserve_pinned(ctx, out_bytes + small_bytes));
+    uint8_t* hp = (uint8_t*)ctx->h_pin;
+    VO_CUDA(ctx, cudaMemcpyAsync(hp, d_out, out_bytes + small_bytes, cudaMemcpyDeviceToHost, ctx->stream));   // corners | small block are adjacent
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    const int* small = (const int*)(hp + out_bytes);
+    for (int s = 0; s < nb; ++s) {
+        if (small[s * VO_GFTT_SMALL + 1] > VO_GFTT_BATCH_CAP)
+            return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "sequence %d: %d corner candidates exceed the batched path's limit of %d (use the per-image call)",
+                              s, small[s * VO_GFTT_SMALL + 1], VO_GFTT_BATCH_CAP);
+        const int n = small[s * VO_GFTT_SMALL + 2];
+        n_corners[s] = n;
+        memcpy(corners + (size_t)s * max_corners * 2, hp + (size_t)s * b_out, (size_t)n * 8);
+    }
     return 0;
 }
 

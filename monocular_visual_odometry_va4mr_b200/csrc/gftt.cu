@@ -24,11 +24,14 @@ __device__ __forceinline__ int refl101(int p, int len)
 
 // img: bordered level-0 (REFLECT_101 border materialised), base -> pixel (0,0)
 __global__ void __launch_bounds__(256)
-gftt_cov_kernel(const uint8_t* __restrict__ img, int pitch, int w, int h, float k0, float k1, float* __restrict__ cov)
+gftt_cov_kernel(const uint8_t* __restrict__ img, size_t img_stride, int pitch, int w, int h, float k0, float k1,
+                float* __restrict__ cov)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
+    img += blockIdx.z * img_stride;                       // one image per blockIdx.z (batched detection)
+    cov += (size_t)blockIdx.z * 3 * w * h;
     const uint8_t* r0 = img + (long long)(y - 1) * pitch + x;
     const uint8_t* r1 = r0 + pitch;
     const uint8_t* r2 = r1 + pitch;
@@ -55,10 +58,10 @@ gftt_cov_kernel(const uint8_t* __restrict__ img, int pitch, int w, int h, float 
 // 3x3 box filter of the three covariance planes exactly as cv2's boxFilter<float -> double -> float>
 // runs it: row sums in double, then a RUNNING column sum in double (SUM += entering row, emit,
 // SUM -= leaving row) whose rounding history is part of the result -- so the sum down a column is a
-// serial chain.  Split in three so that only the chain itself is serial:
-//   gftt_rowsum_kernel   rs[yy+1][ch][x] = double row sum of row yy (REFLECT_101), yy = -1 .. h  (parallel)
-//   gftt_colsum_kernel   one thread per (column, plane): the chain, prefetching 8 rows ahead
+// serial chain.  Split so that only the chain itself is serial:
+//   gftt_colsum_kernel   one thread per (column, plane): double row sums formed on the fly + the chain, prefetching 8 rows ahead
 //   gftt_eig_kernel      a + c - sqrt((a - c)^2 + b^2) and the global maximum                   (parallel)
+// single-image path: parallel double row sums, then the chain with one coalesced load per step
 __global__ void __launch_bounds__(256)
 gftt_rowsum_kernel(const float* __restrict__ cov, int w, int h, double* __restrict__ rs)
 {
@@ -73,7 +76,7 @@ gftt_rowsum_kernel(const float* __restrict__ cov, int w, int h, double* __restri
 }
 
 __global__ void __launch_bounds__(32)
-gftt_colsum_kernel(const double* __restrict__ rs, int w, int h, float* __restrict__ box /* [3][h][w] */)
+gftt_colsum_rs_kernel(const double* __restrict__ rs, int w, int h, float* __restrict__ box /* [3][h][w] */)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 3 * w) return;
@@ -106,10 +109,56 @@ gftt_colsum_kernel(const double* __restrict__ rs, int w, int h, float* __restric
     }
 }
 
+// one thread per (column, plane): the double row sum of each entering row is formed on the fly from the three
+// neighbouring covariance values (cached: the three planes of a pixel share a line), then joins the chain
+__global__ void __launch_bounds__(32)
+gftt_colsum_kernel(const float* __restrict__ cov, int w, int h, float* __restrict__ box /* [3][h][w] */)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * w) return;
+    cov += (size_t)blockIdx.y * 3 * w * h;
+    box += (size_t)blockIdx.y * 3 * w * h;
+    const int x = t / 3, ch = t - x * 3;                   // the three planes of a column sit in adjacent lanes
+    const int xm = refl101(x - 1, w), xp = refl101(x + 1, w);
+    auto rowsum = [&](int yy) {
+        const float* r = cov + 3 * (size_t)refl101(yy, h) * w + ch;
+        return __dadd_rn(__dadd_rn((double)r[3 * xm], (double)r[3 * x]), (double)r[3 * xp]);
+    };
+    float* out = box + (size_t)ch * w * h + x;
+    double prev1 = rowsum(-1), prev0 = rowsum(0);
+    double SUM = __dadd_rn(__dadd_rn(0., prev1), prev0);
+    constexpr int RB = 8;
+    double nxt[RB];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) nxt[k] = rowsum(k + 1);
+    for (int y0 = 0; y0 < h; y0 += RB) {
+        double blk[RB];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) blk[k] = nxt[k];
+        if (y0 + RB < h) {
+#pragma unroll
+            for (int k = 0; k < RB; ++k) nxt[k] = rowsum(y0 + RB + k + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const int y = y0 + k;
+            if (y < h) {
+                const double s0 = __dadd_rn(SUM, blk[k]);
+                out[(size_t)y * w] = (float)s0;
+                SUM = __dsub_rn(s0, prev1);
+                prev1 = prev0; prev0 = blk[k];
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
-gftt_eig_kernel(const float* __restrict__ box, int w, int h, float* __restrict__ eig, int* __restrict__ max_bits)
+gftt_eig_kernel(const float* __restrict__ box, int w, int h, float* __restrict__ eig, int* __restrict__ max_bits, int small_stride)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, npx = (size_t)w * h;
+    box += (size_t)blockIdx.y * 3 * npx;
+    eig += (size_t)blockIdx.y * npx;
+    max_bits += blockIdx.y * small_stride;
     float v = 0.f;
     if (i < npx) {
         const float a = __fmul_rn(box[i], 0.5f), b = box[npx + i], c = __fmul_rn(box[2 * npx + i], 0.5f);
@@ -117,17 +166,30 @@ gftt_eig_kernel(const float* __restrict__ box, int w, int h, float* __restrict__
         v = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
         eig[i] = v;
     }
-    // eig >= 0 up to rounding; negative values never win the max (cv2's max would be >= 0 too)
+    // eig >= 0 up to rounding; negative values never win the max (cv2's max would be >= 0 too).
+    // One atomic per CTA, and only when it can raise the running maximum (a batch has 64 hot addresses).
+    __shared__ float s_max[8];
     float vmax = fmaxf(v, 0.f);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(max_bits, __float_as_int(vmax));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = vmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = s_max[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) m = fmaxf(m, s_max[k]);
+        if (m > __int_as_float(*(volatile int*)max_bits)) atomicMax(max_bits, __float_as_int(m));
+    }
 }
 
 __global__ void __launch_bounds__(256)
 gftt_candidates_kernel(const float* __restrict__ eig, int w, int h, const int* __restrict__ max_bits, double quality,
-                       unsigned long long* __restrict__ keys, int* __restrict__ n_keys, int cap)
+                       unsigned long long* __restrict__ keys, int* __restrict__ n_keys, int cap, int small_stride)
 {
+    eig += (size_t)blockIdx.z * w * h;
+    max_bits += blockIdx.z * small_stride;
+    n_keys += blockIdx.z * small_stride;
+    keys += (size_t)blockIdx.z * cap;
     const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
     bool is_c = false;
@@ -155,9 +217,12 @@ gftt_candidates_kernel(const float* __restrict__ eig, int w, int h, const int* _
 // descending order of the 64-bit keys = (value desc, address desc); keys are unique
 __global__ void __launch_bounds__(256)
 gftt_rank_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ n_keys, int cap,
-                 unsigned long long* __restrict__ sorted)
+                 unsigned long long* __restrict__ sorted, int small_stride)
 {
     __shared__ unsigned long long tile[1024];
+    keys += (size_t)blockIdx.y * cap;
+    sorted += (size_t)blockIdx.y * cap;
+    n_keys += blockIdx.y * small_stride;
     const int n = min(*n_keys, cap);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x * blockDim.x >= n) return;
@@ -267,9 +332,13 @@ gftt_select_kernel(const unsigned long long* __restrict__ sorted, const int* __r
 __global__ void __launch_bounds__(256)
 gftt_select_smem_kernel(const unsigned long long* __restrict__ sorted, const int* __restrict__ n_keys, int cap, int w, int h,
                         int max_corners, double min_dist, int cell, int gw, int gh, float* __restrict__ corners,
-                        int* __restrict__ n_out)
+                        int* __restrict__ n_out, int small_stride, size_t out_stride)
 {
     extern __shared__ uint4 s_cells[];
+    sorted += (size_t)blockIdx.x * cap;                   // one CTA per image
+    n_keys += blockIdx.x * small_stride;
+    n_out += blockIdx.x * small_stride;
+    corners += blockIdx.x * out_stride;
     for (int i = threadIdx.x; i < gw * gh; i += blockDim.x) s_cells[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     __syncthreads();
     if (threadIdx.x >= 32) return;
@@ -398,13 +467,13 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
     const double scale = 1.0 / (4.0 * block_size * 255.0);
     {
         dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
-        gftt_cov_kernel<<<grd, blk, 0, ctx->stream>>>(d_img, g.pitch[0], w, h, (float)scale, (float)(2.0 * scale), d_cov);
+        gftt_cov_kernel<<<grd, blk, 0, ctx->stream>>>(d_img, 0, g.pitch[0], w, h, (float)scale, (float)(2.0 * scale), d_cov);
         gftt_rowsum_kernel<<<dim3((w + 255) / 256, h + 2), 256, 0, ctx->stream>>>(d_cov, w, h, d_rs);
-        gftt_colsum_kernel<<<(3 * w + 31) / 32, 32, 0, ctx->stream>>>(d_rs, w, h, d_box);
-        gftt_eig_kernel<<<(int)((npx + 255) / 256), 256, 0, ctx->stream>>>(d_box, w, h, d_eig, d_small);
+        gftt_colsum_rs_kernel<<<(3 * w + 31) / 32, 32, 0, ctx->stream>>>(d_rs, w, h, d_box);
+        gftt_eig_kernel<<<(int)((npx + 255) / 256), 256, 0, ctx->stream>>>(d_box, w, h, d_eig, d_small, 0);
         ctx->launches += 2;
         dim3 grd2((w - 2 + 31) / 32, (h - 2 + 7) / 8);
-        gftt_candidates_kernel<<<grd2, blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys, d_small + 1, cap);
+        gftt_candidates_kernel<<<grd2, blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys, d_small + 1, cap, 0);
         ctx->launches += 3;
     }
     // the candidate count decides the sort; reading it back costs one small sync (the call is synchronous anyway)
@@ -415,7 +484,7 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
     if (n_keys == 0) { *n_out = 0; return 0; }
     const unsigned long long* d_order = d_sorted;
     if (n_keys <= 32768) {
-        gftt_rank_kernel<<<(n_keys + 255) / 256, 256, 0, ctx->stream>>>(d_keys, d_small + 1, cap, d_sorted);
+        gftt_rank_kernel<<<(n_keys + 255) / 256, 256, 0, ctx->stream>>>(d_keys, d_small + 1, cap, d_sorted, 0);
         ctx->launches++;
     } else {
         int np = 1;
@@ -433,7 +502,7 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
         if (cell_smem > 48 * 1024)
             VO_CUDA(ctx, cudaFuncSetAttribute(gftt_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
         gftt_select_smem_kernel<<<1, 256, cell_smem, ctx->stream>>>(d_order, d_small + 1, cap, w, h, max_corners, min_dist, cell, gw,
-                                                                    gh, d_out, d_small + 2);
+                                                                    gh, d_out, d_small + 2, 0, 0);
     } else {
         gftt_select_kernel<<<1, 32, 0, ctx->stream>>>(d_order, d_small + 1, cap, w, h, max_corners, min_dist, cell, gw, gh, d_cnt,
                                                       d_pts, d_out, d_small + 2);
@@ -452,5 +521,62 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
         memcpy(corners_xy, ctx->h_pin, (size_t)n * 8);
     }
     *n_out = n;
+    return 0;
+}
+
+// Batched detection on device-resident bordered level-0 images (one per sequence, `img_stride` bytes apart):
+// every kernel above with the image index in the grid, one selection CTA per image, no intermediate host
+// synchronisation (at most GFTT_BATCH_CAP candidates per image, ranked by counting).
+#define GFTT_BATCH_CAP VO_GFTT_BATCH_CAP
+#define GFTT_SMALL VO_GFTT_SMALL
+
+size_t vo_gftt_batch_workspace(int rows, int cols, int batch, int max_corners)
+{
+    const size_t npx = (size_t)rows * cols;
+    return 2 * vo_align(npx * 12 * batch, 256) + vo_align(npx * 4 * batch, 256) +
+           (size_t)batch * (2 * vo_align((size_t)GFTT_BATCH_CAP * 8, 256) + vo_align((size_t)max_corners * 8, 256)) +
+           vo_align((size_t)batch * GFTT_SMALL * sizeof(int), 256);
+}
+
+int vo_gftt_batch_launch(b200vo_ctx* ctx, const uint8_t* d_img0, size_t img_stride, int pitch, int rows, int cols, int batch,
+                         int max_corners, double quality, double min_dist, void* ws, float** d_corners_out, int** d_small_out)
+{
+    const int w = cols, h = rows;
+    const size_t npx = (size_t)w * h;
+    if (!(quality > 0) || min_dist < 0 || max_corners < 0)
+        return vo_set_err(ctx, B200VO_E_BADARG, "qualityLevel > 0 && minDistance >= 0 && maxCorners >= 0");
+    const int cell = (int)llrint(min_dist);
+    const int gw = cell > 0 ? (w + cell - 1) / cell : 0, gh = cell > 0 ? (h + cell - 1) / cell : 0;
+    const size_t cell_smem = (size_t)gw * gh * sizeof(uint4);
+    if (min_dist < 1 || max_corners <= 0 || cell_smem > 200 * 1024 || rows < 3 || cols < 3 || cols >= 65536 || rows >= 32768)
+        return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "batched detection needs minDistance >= 1, maxCorners > 0 and a cell grid that fits shared memory");
+    // per-image planes are tightly packed (the kernels derive the image offsets from w, h)
+    const size_t b_keys = vo_align((size_t)GFTT_BATCH_CAP * 8, 256), b_out = vo_align((size_t)max_corners * 8, 256);
+    uint8_t* d = (uint8_t*)ws;
+    float* d_cov = (float*)d; d += vo_align(npx * 12 * batch, 256);
+    float* d_box = (float*)d; d += vo_align(npx * 12 * batch, 256);
+    float* d_eig = (float*)d; d += vo_align(npx * 4 * batch, 256);
+    unsigned long long* d_keys = (unsigned long long*)d; d += b_keys * batch;
+    unsigned long long* d_sorted = (unsigned long long*)d; d += b_keys * batch;
+    float* d_out = (float*)d; d += b_out * batch;
+    int* d_small = (int*)d;
+    VO_CUDA(ctx, cudaMemsetAsync(d_small, 0, (size_t)batch * GFTT_SMALL * sizeof(int), ctx->stream));
+    const double scale = 1.0 / (4.0 * 3 * 255.0);
+    dim3 blk(32, 8);
+    gftt_cov_kernel<<<dim3((w + 31) / 32, (h + 7) / 8, batch), blk, 0, ctx->stream>>>(d_img0, img_stride, pitch, w, h, (float)scale,
+                                                                                      (float)(2.0 * scale), d_cov);
+    gftt_colsum_kernel<<<dim3((3 * w + 31) / 32, batch), 32, 0, ctx->stream>>>(d_cov, w, h, d_box);
+    gftt_eig_kernel<<<dim3((unsigned)((npx + 255) / 256), batch), 256, 0, ctx->stream>>>(d_box, w, h, d_eig, d_small, GFTT_SMALL);
+    gftt_candidates_kernel<<<dim3((w - 2 + 31) / 32, (h - 2 + 7) / 8, batch), blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys,
+                                                                                                    d_small + 1, GFTT_BATCH_CAP, GFTT_SMALL);
+    gftt_rank_kernel<<<dim3(GFTT_BATCH_CAP / 256, batch), 256, 0, ctx->stream>>>(d_keys, d_small + 1, GFTT_BATCH_CAP, d_sorted, GFTT_SMALL);
+    if (cell_smem > 48 * 1024)
+        VO_CUDA(ctx, cudaFuncSetAttribute(gftt_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
+    gftt_select_smem_kernel<<<batch, 256, cell_smem, ctx->stream>>>(d_sorted, d_small + 1, GFTT_BATCH_CAP, w, h, max_corners, min_dist, cell,
+                                                                    gw, gh, d_out, d_small + 2, GFTT_SMALL, b_out / 4);
+    ctx->launches += 6;
+    VO_CUDA(ctx, cudaGetLastError());
+    *d_corners_out = d_out;
+    *d_small_out = d_small;
     return 0;
 }

@@ -95,6 +95,13 @@ Pyramid vo_pyramid_at(const PyrGeom& g, uint8_t* slab);
 int vo_build_pyramids(b200vo_ctx* ctx, const uint8_t* d_raw, size_t raw_stride, int rows, int cols,
                       const PyrGeom& g, uint8_t* d_slab, size_t slab_stride, int batch);
 
+// ---- gftt.cu: detection on device-resident bordered level-0 images, one per batch entry ----
+#define VO_GFTT_SMALL 4          // ints per image in the result block: max bits | n candidates | n corners | spare
+#define VO_GFTT_BATCH_CAP 32768  // candidates per image the batched path can rank
+size_t vo_gftt_batch_workspace(int rows, int cols, int batch, int max_corners);
+int vo_gftt_batch_launch(b200vo_ctx* ctx, const uint8_t* d_img0, size_t img_stride, int pitch, int rows, int cols, int batch,
+                         int max_corners, double quality, double min_dist, void* ws, float** d_corners_out, int** d_small_out);
+
 // ---- klt.cu ----
 struct KltPointSet {
     int cap;            // slots per sequence

@@ -202,3 +202,30 @@ def test_batch_ragged_counts(wl):
                 assert int(o["n_inliers"][s]) == len(inl)
                 assert np.array_equal(np.flatnonzero(o["inlier_mask"][s]), np.flatnonzero(keep)[inl.ravel()])
     sb.close()
+
+
+def test_batch_good_features_equals_per_image_call(wl):
+    """b200vo_batch_good_features on the resident frames == cv2.goodFeaturesToTrack per image (reference :256 options)."""
+    opts = workload.REFERENCE_OPTIONS["kitti"]
+    sb = SequenceBatch(wl.batch, wl.h, wl.w, wl.K, win=opts["win"], max_level=opts["max_level"], criteria=opts["criteria"],
+                       max_landmarks=wl.L, max_candidates=wl.Cn)
+    sb.prime(wl.frames[0])
+    for frame_idx, (mc, q, md) in ((0, (1400, 0.1, 10.0)), (1, (300, 0.03, 7.0))):
+        if frame_idx:     # after a step the NEW frames are the resident ones
+            sb.step(wl.frames[1], wl.lm_pts[0], wl.lm_obj[0], wl.n_lm[0], wl.cand_pts[0], wl.n_cand[0])
+        corners, n = sb.good_features(mc, q, md)
+        assert corners.shape == (wl.batch, mc, 2) and n.shape == (wl.batch,)
+        for s in range(wl.batch):
+            ref = cv2_compat.goodFeaturesToTrack(wl.frames[frame_idx, s], mc, q, md, blockSize=3)
+            ref = np.zeros((0, 2), np.float32) if ref is None else ref.reshape(-1, 2)
+            assert int(n[s]) == len(ref) and np.array_equal(corners[s, :n[s]], ref), (frame_idx, s)
+            try:
+                import cv2
+            except ImportError:
+                continue
+            c = cv2.goodFeaturesToTrack(wl.frames[frame_idx, s], mc, q, md, blockSize=3)
+            assert np.array_equal(corners[s, :n[s]], c.reshape(-1, 2))
+    from monocular_visual_odometry_va4mr_b200._lib import B200VOError
+    with pytest.raises((B200VOError, NotImplementedError)):
+        sb.good_features(0, 0.1, 10.0)
+    sb.close()
