@@ -152,6 +152,100 @@ gftt_colsum_kernel(const float* __restrict__ cov, int w, int h, float* __restric
     }
 }
 
+// Batched path: covariance, box filter and eigenvalue in ONE pass down the columns.  A warp owns 30 adjacent
+// columns (lanes 1..30; lanes 0 and 31 carry the REFLECT_101 neighbours x0-1 and x0+30).  Per image row every lane
+// forms the three covariance products of its column exactly as gftt_cov_kernel does, the double row sums come from
+// the neighbouring lanes by shuffle, and the three running column sums, the eigenvalue and the per-image maximum
+// follow -- the covariance and box planes (24 B per pixel) never exist in memory.
+#define GF_COLS 30
+__global__ void __launch_bounds__(32)
+gftt_fused_eig_kernel(const uint8_t* __restrict__ img, size_t img_stride, int pitch, int w, int h, float k0, float k1,
+                      float* __restrict__ eig, int* __restrict__ max_bits, int small_stride)
+{
+    const int lane = threadIdx.x;
+    img += blockIdx.y * img_stride;
+    eig += (size_t)blockIdx.y * w * h;
+    max_bits += blockIdx.y * small_stride;
+    const int xv = blockIdx.x * GF_COLS + lane - 1;            // virtual column (may be -1 or >= w)
+    const int x = refl101(xv < w + 1 ? xv : w, w);              // column whose covariance this lane forms
+    const bool owner = lane >= 1 && lane <= GF_COLS && xv < w;
+    const bool fused_cols = x < (w & ~31);
+    auto cov_row = [&](int yy, float* c) {                      // covariance products of pixel (x, refl(yy))
+        const int y = refl101(yy, h);
+        const uint8_t* r0 = img + (long long)(y - 1) * pitch + x;
+        const uint8_t* r1 = r0 + pitch;
+        const uint8_t* r2 = r1 + pitch;
+        const int a0 = r0[-1], a1 = r0[0], a2 = r0[1];
+        const int b0 = r1[-1], b2 = r1[1];
+        const int c0 = r2[-1], c1 = r2[0], c2 = r2[1];
+        const int s0 = a2 - a0, s1 = b2 - b0, s2 = c2 - c0;
+        const float dx = __fmaf_rn((float)(s0 + s2), k0, __fmul_rn((float)s1, k1));
+        float rt, rb;
+        if (fused_cols) {
+            rt = __fmaf_rn(k0, (float)a2, __fmaf_rn(k1, (float)a1, __fmul_rn(k0, (float)a0)));
+            rb = __fmaf_rn(k0, (float)c2, __fmaf_rn(k1, (float)c1, __fmul_rn(k0, (float)c0)));
+        } else {
+            rt = __fadd_rn(__fadd_rn(__fmul_rn(k0, (float)a0), __fmul_rn(k1, (float)a1)), __fmul_rn(k0, (float)a2));
+            rb = __fadd_rn(__fadd_rn(__fmul_rn(k0, (float)c0), __fmul_rn(k1, (float)c1)), __fmul_rn(k0, (float)c2));
+        }
+        const float dy = __fsub_rn(rb, rt);
+        c[0] = __fmul_rn(dx, dx); c[1] = __fmul_rn(dx, dy); c[2] = __fmul_rn(dy, dy);
+    };
+    auto row_sums = [&](const float* c, double* rs) {           // double sum of the left, own and right column
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {                        // one conversion per value, the doubles travel
+            const double m = (double)c[ch];
+            const double l = __shfl_up_sync(0xffffffffu, m, 1), r = __shfl_down_sync(0xffffffffu, m, 1);
+            rs[ch] = __dadd_rn(__dadd_rn(l, m), r);
+        }
+    };
+    float c[3];
+    double prev1[3], prev0[3], SUM[3];
+    cov_row(-1, c); row_sums(c, prev1);
+    cov_row(0, c); row_sums(c, prev0);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) SUM[ch] = __dadd_rn(__dadd_rn(0., prev1[ch]), prev0[ch]);
+    float vmax = 0.f;
+    constexpr int RB = 4;
+    float nxt[RB][3];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) cov_row(k + 1, nxt[k]);
+    for (int y0 = 0; y0 < h; y0 += RB) {
+        float blk[RB][3];
+#pragma unroll
+        for (int k = 0; k < RB; ++k)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) blk[k][ch] = nxt[k][ch];
+        if (y0 + RB < h) {
+#pragma unroll
+            for (int k = 0; k < RB; ++k) cov_row(y0 + RB + k + 1, nxt[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const int y = y0 + k;
+            if (y < h) {                                         // warp-uniform
+                double cur[3];
+                row_sums(blk[k], cur);
+                float bx[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const double s0 = __dadd_rn(SUM[ch], cur[ch]);
+                    bx[ch] = (float)s0;
+                    SUM[ch] = __dsub_rn(s0, prev1[ch]);
+                    prev1[ch] = prev0[ch]; prev0[ch] = cur[ch];
+                }
+                const float a = __fmul_rn(bx[0], 0.5f), b = bx[1], cc = __fmul_rn(bx[2], 0.5f);
+                const float t = __fsub_rn(a, cc);
+                const float v = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+                if (owner) { eig[(size_t)y * w + xv] = v; vmax = fmaxf(vmax, v); }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > __int_as_float(*(volatile int*)max_bits)) atomicMax(max_bits, __float_as_int(vmax));
+}
+
 __global__ void __launch_bounds__(256)
 gftt_eig_kernel(const float* __restrict__ box, int w, int h, float* __restrict__ eig, int* __restrict__ max_bits, int small_stride)
 {
@@ -533,7 +627,7 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
 size_t vo_gftt_batch_workspace(int rows, int cols, int batch, int max_corners)
 {
     const size_t npx = (size_t)rows * cols;
-    return 2 * vo_align(npx * 12 * batch, 256) + vo_align(npx * 4 * batch, 256) +
+    return vo_align(npx * 4 * batch, 256) +
            (size_t)batch * (2 * vo_align((size_t)GFTT_BATCH_CAP * 8, 256) + vo_align((size_t)max_corners * 8, 256)) +
            vo_align((size_t)batch * GFTT_SMALL * sizeof(int), 256);
 }
@@ -553,8 +647,6 @@ int vo_gftt_batch_launch(b200vo_ctx* ctx, const uint8_t* d_img0, size_t img_stri
     // per-image planes are tightly packed (the kernels derive the image offsets from w, h)
     const size_t b_keys = vo_align((size_t)GFTT_BATCH_CAP * 8, 256), b_out = vo_align((size_t)max_corners * 8, 256);
     uint8_t* d = (uint8_t*)ws;
-    float* d_cov = (float*)d; d += vo_align(npx * 12 * batch, 256);
-    float* d_box = (float*)d; d += vo_align(npx * 12 * batch, 256);
     float* d_eig = (float*)d; d += vo_align(npx * 4 * batch, 256);
     unsigned long long* d_keys = (unsigned long long*)d; d += b_keys * batch;
     unsigned long long* d_sorted = (unsigned long long*)d; d += b_keys * batch;
@@ -563,10 +655,8 @@ int vo_gftt_batch_launch(b200vo_ctx* ctx, const uint8_t* d_img0, size_t img_stri
     VO_CUDA(ctx, cudaMemsetAsync(d_small, 0, (size_t)batch * GFTT_SMALL * sizeof(int), ctx->stream));
     const double scale = 1.0 / (4.0 * 3 * 255.0);
     dim3 blk(32, 8);
-    gftt_cov_kernel<<<dim3((w + 31) / 32, (h + 7) / 8, batch), blk, 0, ctx->stream>>>(d_img0, img_stride, pitch, w, h, (float)scale,
-                                                                                      (float)(2.0 * scale), d_cov);
-    gftt_colsum_kernel<<<dim3((3 * w + 31) / 32, batch), 32, 0, ctx->stream>>>(d_cov, w, h, d_box);
-    gftt_eig_kernel<<<dim3((unsigned)((npx + 255) / 256), batch), 256, 0, ctx->stream>>>(d_box, w, h, d_eig, d_small, GFTT_SMALL);
+    gftt_fused_eig_kernel<<<dim3((w + GF_COLS - 1) / GF_COLS, batch), 32, 0, ctx->stream>>>(d_img0, img_stride, pitch, w, h, (float)scale,
+                                                                                            (float)(2.0 * scale), d_eig, d_small, GFTT_SMALL);
     gftt_candidates_kernel<<<dim3((w - 2 + 31) / 32, (h - 2 + 7) / 8, batch), blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys,
                                                                                                     d_small + 1, GFTT_BATCH_CAP, GFTT_SMALL);
     gftt_rank_kernel<<<dim3(GFTT_BATCH_CAP / 256, batch), 256, 0, ctx->stream>>>(d_keys, d_small + 1, GFTT_BATCH_CAP, d_sorted, GFTT_SMALL);
@@ -574,7 +664,7 @@ int vo_gftt_batch_launch(b200vo_ctx* ctx, const uint8_t* d_img0, size_t img_stri
         VO_CUDA(ctx, cudaFuncSetAttribute(gftt_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
     gftt_select_smem_kernel<<<batch, 256, cell_smem, ctx->stream>>>(d_sorted, d_small + 1, GFTT_BATCH_CAP, w, h, max_corners, min_dist, cell,
                                                                     gw, gh, d_out, d_small + 2, GFTT_SMALL, b_out / 4);
-    ctx->launches += 6;
+    ctx->launches += 4;
     VO_CUDA(ctx, cudaGetLastError());
     *d_corners_out = d_out;
     *d_small_out = d_small;
