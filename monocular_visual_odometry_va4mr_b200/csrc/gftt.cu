@@ -199,48 +199,85 @@ gftt_fused_eig_kernel(const uint8_t* __restrict__ img, size_t img_stride, int pi
             rs[ch] = __dadd_rn(__dadd_rn(l, m), r);
         }
     };
+    // covariance products from a 3 x 3 pixel window held in registers (a*: row above, b*: own row, c*: row below)
+    auto cov_win = [&](int a0, int a1, int a2, int b0, int b2, int c0, int c1, int c2, float* c) {
+        const int s0 = a2 - a0, s1 = b2 - b0, s2 = c2 - c0;
+        const float dx = __fmaf_rn((float)(s0 + s2), k0, __fmul_rn((float)s1, k1));
+        float rt, rb;
+        if (fused_cols) {
+            rt = __fmaf_rn(k0, (float)a2, __fmaf_rn(k1, (float)a1, __fmul_rn(k0, (float)a0)));
+            rb = __fmaf_rn(k0, (float)c2, __fmaf_rn(k1, (float)c1, __fmul_rn(k0, (float)c0)));
+        } else {
+            rt = __fadd_rn(__fadd_rn(__fmul_rn(k0, (float)a0), __fmul_rn(k1, (float)a1)), __fmul_rn(k0, (float)a2));
+            rb = __fadd_rn(__fadd_rn(__fmul_rn(k0, (float)c0), __fmul_rn(k1, (float)c1)), __fmul_rn(k0, (float)c2));
+        }
+        const float dy = __fsub_rn(rb, rt);
+        c[0] = __fmul_rn(dx, dx); c[1] = __fmul_rn(dx, dy); c[2] = __fmul_rn(dy, dy);
+    };
     float c[3];
     double prev1[3], prev0[3], SUM[3];
-    cov_row(-1, c); row_sums(c, prev1);
+    cov_row(-1, c); row_sums(c, prev1);       // leaving row of y = 0: image row 1
     cov_row(0, c); row_sums(c, prev0);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) SUM[ch] = __dadd_rn(__dadd_rn(0., prev1[ch]), prev0[ch]);
     float vmax = 0.f;
-    constexpr int RB = 4;
-    float nxt[RB][3];
-#pragma unroll
-    for (int k = 0; k < RB; ++k) cov_row(k + 1, nxt[k]);
-    for (int y0 = 0; y0 < h; y0 += RB) {
-        float blk[RB][3];
-#pragma unroll
-        for (int k = 0; k < RB; ++k)
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) blk[k][ch] = nxt[k][ch];
-        if (y0 + RB < h) {
-#pragma unroll
-            for (int k = 0; k < RB; ++k) cov_row(y0 + RB + k + 1, nxt[k]);
-        }
+    // Entering rows yy = 1 .. h-1 are consecutive image rows: a sliding window needs three new pixels per row.
+    // The pixel triples of the next RB rows are fetched while the chain of this block runs.  The last entering
+    // row (yy = h) is image row h-2 again and is formed on its own.
+    const uint8_t* prow = img + x;                                   // pixel (x, 0); rows -1 .. h exist (border)
+    int w0[3], w1[3], w2[3];                                         // window rows: (yy-1), yy, (yy+1) for the row being formed
+    {
+        const uint8_t* r = prow;                                     // row 0
+        w0[0] = r[-1]; w0[1] = r[0]; w0[2] = r[1];
+        r += pitch;                                                  // row 1
+        w1[0] = r[-1]; w1[1] = r[0]; w1[2] = r[1];
+    }
+    constexpr int RB = 8;
+    int nx0[RB], nx1[RB], nx2[RB];
+    auto fetch = [&](int yy_first) {                                 // pixel rows yy_first+1 .. yy_first+RB (the row BELOW each entering row)
 #pragma unroll
         for (int k = 0; k < RB; ++k) {
-            const int y = y0 + k;
-            if (y < h) {                                         // warp-uniform
-                double cur[3];
-                row_sums(blk[k], cur);
-                float bx[3];
+            const int pr = min(yy_first + k + 1, h);                 // row h is the materialised border row
+            const uint8_t* r = prow + (long long)pr * pitch;
+            nx0[k] = r[-1]; nx1[k] = r[0]; nx2[k] = r[1];
+        }
+    };
+    fetch(1);
+    auto emit = [&](int y, const float* cv) {                        // entering row formed: advance the three chains, write eig(y)
+        double cur[3];
+        row_sums(cv, cur);
+        float bx[3];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const double s0 = __dadd_rn(SUM[ch], cur[ch]);
-                    bx[ch] = (float)s0;
-                    SUM[ch] = __dsub_rn(s0, prev1[ch]);
-                    prev1[ch] = prev0[ch]; prev0[ch] = cur[ch];
-                }
-                const float a = __fmul_rn(bx[0], 0.5f), b = bx[1], cc = __fmul_rn(bx[2], 0.5f);
-                const float t = __fsub_rn(a, cc);
-                const float v = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
-                if (owner) { eig[(size_t)y * w + xv] = v; vmax = fmaxf(vmax, v); }
+        for (int ch = 0; ch < 3; ++ch) {
+            const double s0 = __dadd_rn(SUM[ch], cur[ch]);
+            bx[ch] = (float)s0;
+            SUM[ch] = __dsub_rn(s0, prev1[ch]);
+            prev1[ch] = prev0[ch]; prev0[ch] = cur[ch];
+        }
+        const float a = __fmul_rn(bx[0], 0.5f), b = bx[1], cc = __fmul_rn(bx[2], 0.5f);
+        const float t = __fsub_rn(a, cc);
+        const float v = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+        if (owner) { eig[(size_t)y * w + xv] = v; vmax = fmaxf(vmax, v); }
+    };
+    for (int yy0 = 1; yy0 <= h - 1; yy0 += RB) {                     // entering rows yy0 .. yy0+RB-1 (output rows yy-1)
+        int b0[RB], b1[RB], b2[RB];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) { b0[k] = nx0[k]; b1[k] = nx1[k]; b2[k] = nx2[k]; }
+        if (yy0 + RB <= h - 1) fetch(yy0 + RB);
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const int yy = yy0 + k;
+            if (yy <= h - 1) {                                       // warp-uniform
+                float cv[3];
+                cov_win(w0[0], w0[1], w0[2], w1[0], w1[2], b0[k], b1[k], b2[k], cv);
+                emit(yy - 1, cv);
+                w0[0] = w1[0]; w0[1] = w1[1]; w0[2] = w1[2];
+                w1[0] = b0[k]; w1[1] = b1[k]; w1[2] = b2[k];
             }
         }
     }
+    cov_row(h, c);                                                   // last entering row: image row h-2
+    emit(h - 1, c);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     if (lane == 0 && vmax > __int_as_float(*(volatile int*)max_bits)) atomicMax(max_bits, __float_as_int(vmax));
