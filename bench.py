@@ -267,6 +267,10 @@ def main():
     sb.prime(wl.frames[order[0]])
     for t in range(W):
         dev_step(t)
+    if world > 1:   # the trajectory gather of the timed region runs once untimed first (NCCL sets its channels up lazily)
+        stream.synchronize()
+        sharding.gather_trajectories(d_out["pose"], world)
+        torch.cuda.current_stream().synchronize()
     barrier()
     clk_samples, stop = [], threading.Event()
     th = threading.Thread(target=clocks_sampler, args=(stop, clk_samples, local), daemon=True)
