@@ -119,6 +119,34 @@ __device__ __forceinline__ void interp_run8(const uint8_t* img, int off, int sh8
     I[7] = (int)(dp2a_hi_u(wb, bs1, dp2a_hi_u(wt, ts1, R)) >> (W_BITS - 5));
 }
 
+// Same with the image given as a 32-bit shared-memory address that lives in a register (the iteration loop:
+// the compiler otherwise rematerialises the warp's shared-memory base from %tid / %cluster_ctaid every iteration).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int RS>
+__device__ __forceinline__ void interp_run8_s(uint32_t img_s, int off, int sh8, uint32_t wt, uint32_t wb, int* I)
+{
+    const uint32_t t = img_s + (uint32_t)(off & ~3), b = t + RS;
+    const uint32_t t0 = lds_u32(t), t1 = lds_u32(t + 4), t2 = lds_u32(t + 8), b0 = lds_u32(b), b1 = lds_u32(b + 4), b2 = lds_u32(b + 8);
+    const uint32_t ta0 = __funnelshift_r(t0, t1, sh8), ta1 = __funnelshift_r(t1, t2, sh8), ta2 = t2 >> sh8;
+    const uint32_t ba0 = __funnelshift_r(b0, b1, sh8), ba1 = __funnelshift_r(b1, b2, sh8), ba2 = b2 >> sh8;
+    const uint32_t ts0 = __funnelshift_r(ta0, ta1, 8), ts1 = __funnelshift_r(ta1, ta2, 8);
+    const uint32_t bs0 = __funnelshift_r(ba0, ba1, 8), bs1 = __funnelshift_r(ba1, ba2, 8);
+    const uint32_t R = 1u << (W_BITS - 5 - 1);
+    I[0] = (int)(dp2a_lo_u(wb, ba0, dp2a_lo_u(wt, ta0, R)) >> (W_BITS - 5));
+    I[1] = (int)(dp2a_lo_u(wb, bs0, dp2a_lo_u(wt, ts0, R)) >> (W_BITS - 5));
+    I[2] = (int)(dp2a_hi_u(wb, ba0, dp2a_hi_u(wt, ta0, R)) >> (W_BITS - 5));
+    I[3] = (int)(dp2a_hi_u(wb, bs0, dp2a_hi_u(wt, ts0, R)) >> (W_BITS - 5));
+    I[4] = (int)(dp2a_lo_u(wb, ba1, dp2a_lo_u(wt, ta1, R)) >> (W_BITS - 5));
+    I[5] = (int)(dp2a_lo_u(wb, bs1, dp2a_lo_u(wt, ts1, R)) >> (W_BITS - 5));
+    I[6] = (int)(dp2a_hi_u(wb, ba1, dp2a_hi_u(wt, ta1, R)) >> (W_BITS - 5));
+    I[7] = (int)(dp2a_hi_u(wb, bs1, dp2a_hi_u(wt, ts1, R)) >> (W_BITS - 5));
+}
+
 template <int WW, int WH>
 __global__ void __launch_bounds__(KLT_WARPS * 32, (KV2<WW, WH>::MIN_CTAS))
 klt_kernel_v2(const KltArgs a)
@@ -140,6 +168,8 @@ klt_kernel_v2(const KltArgs a)
     uint8_t* wbase = smem + (size_t)warp * C::PER_WARP;
     uint8_t* patch_buf = wbase;                                  // two buffers of B_PATCH
     uint8_t* jreg = wbase + 2 * C::B_PATCH;
+    uint32_t jreg_s;      // opaque to the compiler: stays in a register instead of being rebuilt per iteration
+    asm volatile("mov.u32 %0, %1;" : "=r"(jreg_s) : "r"((uint32_t)__cvta_generic_to_shared(jreg)));
     int* derx = reinterpret_cast<int*>(wbase + 2 * C::B_PATCH + C::B_J);
     int* dery = derx + C::DS * C::DH;
     short* Iwin = reinterpret_cast<short*>(wbase + 2 * C::B_PATCH + C::B_J + 2 * C::B_DER);
@@ -363,7 +393,7 @@ klt_kernel_v2(const KltArgs a)
             for (int r = 0; r < C::NROUND; ++r) {
                 const int off = joff + ty[r] * C::JS + tx[r];
                 int Iv[8];
-                interp_run8<C::JS>(jreg, off, (off & 3) * 8, jt, jb, Iv);
+                interp_run8_s<C::JS>(jreg_s, off, (off & 3) * 8, jt, jb, Iv);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { sb1 += Iv[k] * gxr[r][k]; sb2 += Iv[k] * gyr[r][k]; }
             }
