@@ -192,6 +192,10 @@ klt_kernel_v2(const KltArgs a)
         if (t >= C::NTASK) { ty[r] = 0; tx[r] = 0; }
     }
 
+    // this lane's byte offsets inside the staged J window, pinned to registers (see jreg_s)
+    int joffl[C::NROUND];
+#pragma unroll
+    for (int r = 0; r < C::NROUND; ++r) asm volatile("mov.s32 %0, %1;" : "=r"(joffl[r]) : "r"(ty[r] * C::JS + tx[r]));
     float outx = 0.f, outy = 0.f;
     int st = 1;
     float e = 0.f;
@@ -199,7 +203,10 @@ klt_kernel_v2(const KltArgs a)
     const float eps_lo = a.eps_lo, eps_hi = a.eps_hi;
 
     for (int level = a.levels - 1; level >= 0; --level) {
-        const int lw = a.w[level], lh = a.h[level], pitch = a.pitch[level];
+        int lw, lh;
+        asm volatile("mov.s32 %0, %1;" : "=r"(lw) : "r"(a.w[level]));
+        asm volatile("mov.s32 %0, %1;" : "=r"(lh) : "r"(a.h[level]));
+        const int pitch = a.pitch[level];
         const uint8_t* I = prev + a.off[level];
         const uint8_t* J = next + a.off[level];
         const float sc = (float)(1.0 / (double)(1 << level));
@@ -391,7 +398,7 @@ klt_kernel_v2(const KltArgs a)
             int sb1 = -c1, sb2 = -c2;
 #pragma unroll
             for (int r = 0; r < C::NROUND; ++r) {
-                const int off = joff + ty[r] * C::JS + tx[r];
+                const int off = joff + joffl[r];
                 int Iv[8];
                 interp_run8_s<C::JS>(jreg_s, off, (off & 3) * 8, jt, jb, Iv);
 #pragma unroll
