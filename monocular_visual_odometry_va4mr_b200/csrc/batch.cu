@@ -453,7 +453,11 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     const size_t q_ni = q_mask + vo_align((size_t)nb * L, 256), out_bytes = q_ni + vo_align((size_t)nb * 4, 256);
     VO_TRY(vo_reserve(ctx, B->raw, f_total));
     VO_TRY(vo_reserve(ctx, B->pts_in, in_bytes));
-    VO_TRY(vo_reserve(ctx, B->outs, out_bytes));
+    {   // slots beyond the live counts are never written by the kernels: give them a defined value (0) once
+        void* before = B->outs.p;
+        VO_TRY(vo_reserve(ctx, B->outs, out_bytes));
+        if (B->outs.p != before) VO_CUDA(ctx, cudaMemsetAsync(B->outs.p, 0, out_bytes, ctx->stream));
+    }
     if (!B->primed) return vo_set_err(ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
     const bool prefetched = frames == nullptr;
     if (prefetched && B->q_count == 0)

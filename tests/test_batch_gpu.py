@@ -229,3 +229,40 @@ def test_batch_good_features_equals_per_image_call(wl):
     with pytest.raises((B200VOError, NotImplementedError)):
         sb.good_features(0, 0.1, 10.0)
     sb.close()
+
+
+@pytest.mark.parametrize("batch", [10, 33])
+def test_batch_chunked_upload_paths(batch):
+    """Batches large enough for the chunked call-by-call upload (ragged last chunk) give the bits of the prefetch form
+    and of the per-call path."""
+    opts = workload.REFERENCE_OPTIONS["kitti"]
+    w2 = workload.TrackWorkload("kitti", batch=batch, n_frames=3, n_landmarks=60, n_candidates=40, n_distinct=2, seed=9,
+                                width=320, height=160, cap_landmarks=64, cap_candidates=64)
+    order, ref = _run_steps(w2, 3, opts, pinned=True)                 # call by call (chunked)
+    sb = SequenceBatch(w2.batch, w2.h, w2.w, w2.K, win=opts["win"], max_level=opts["max_level"], criteria=opts["criteria"],
+                       pnp_iters=opts["pnp_iters"], pnp_reproj_err=opts["pnp_err"], pnp_conf=opts["pnp_conf"],
+                       max_landmarks=w2.L, max_candidates=w2.Cn)
+    frames = sb.pinned_frames(w2.F)
+    frames[:] = w2.frames
+    sb.prime(frames[order[0]])
+    sb.submit_frames(frames[order[1]])
+    for t in range(3):
+        f = order[t]
+        if t + 2 <= 3:
+            sb.submit_frames(frames[order[t + 2]])
+        o = sb.step(None, w2.lm_pts[f], w2.lm_obj[f], w2.n_lm[f], w2.cand_pts[f], w2.n_cand[f])
+        for s_ in range(batch):                                  # live slots (the others are not written by the kernels)
+            nl, nc = int(w2.n_lm[f, s_]), int(w2.n_cand[f, s_])
+            for k in ("lm_next", "lm_status", "inlier_mask"):
+                assert np.array_equal(o[k][s_, :nl], ref[t][k][s_, :nl]), (t, k, s_)
+            for k in ("cand_next", "cand_status"):
+                assert np.array_equal(o[k][s_, :nc], ref[t][k][s_, :nc]), (t, k, s_)
+        for k in ("pose", "pnp_ok", "n_inliers"):
+            assert np.array_equal(o[k], ref[t][k]), (t, k)
+    sb.close()
+    f, g = order[0], order[1]
+    for s in (0, batch // 2, batch - 1):
+        nl = int(w2.n_lm[f, s])
+        p, st, _ = cv2_compat.calcOpticalFlowPyrLK(w2.frames[f, s], w2.frames[g, s], w2.lm_pts[f, s, :nl], None,
+                                                   winSize=opts["win"], maxLevel=opts["max_level"], criteria=opts["criteria"])
+        assert np.array_equal(ref[0]["lm_status"][s, :nl], st.ravel()) and np.array_equal(ref[0]["lm_next"][s, :nl], p)
