@@ -161,7 +161,7 @@ pyr_down_kernel(const uint8_t* __restrict__ slab_src, uint8_t* __restrict__ slab
 
 __global__ void __launch_bounds__(256)
 pyr_down_tma_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __restrict__ slab_dst, size_t slab_stride,
-                    size_t off_d, int dw, int dh, int dpitch)
+                    size_t off_d, int dw, int dh, int dpitch, int fuse_border)
 {
     // source bytes [0,160) and [128,288) of each row; each half starts on a 128-byte boundary (TMA destination)
     __shared__ __align__(128) uint8_t tile[2][(PD_SR * PD_SB + 127) / 128 * 128];
@@ -207,8 +207,32 @@ pyr_down_tma_kernel(const __grid_constant__ CUtensorMap src_map, uint8_t* __rest
         const uint32_t o0 = (uint32_t)((acc[0] + 128) >> 8), o1 = (uint32_t)((acc[1] + 128) >> 8);
         const uint32_t o2 = (uint32_t)((acc[2] + 128) >> 8), o3 = (uint32_t)((acc[3] + 128) >> 8);
         uint8_t* dp = dst + (long long)y * dpitch + x;
-        if (x + 3 < dw) *reinterpret_cast<uint32_t*>(dp) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        const uint32_t word = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        if (x + 3 < dw) *reinterpret_cast<uint32_t*>(dp) = word;
         else { dp[0] = (uint8_t)o0; if (x + 1 < dw) dp[1] = (uint8_t)o1; if (x + 2 < dw) dp[2] = (uint8_t)o2; }
+        // REFLECT_101 ring of this level written by the pixels it mirrors (dw, dh >= VO_BORDER + 2: single bounce):
+        // columns 1..B -> -1..-B and dw-1-B..dw-2 -> dw..dw+B-1, rows likewise, corners by both
+        if (fuse_border && (x <= VO_BORDER || x + 3 >= dw - 1 - VO_BORDER || y <= VO_BORDER || y >= dh - 1 - VO_BORDER)) {
+            auto put_row = [&](int yy) {
+                uint8_t* rowp = dst + (long long)yy * dpitch;
+                if (yy != y) {
+                    if (x + 3 < dw) *reinterpret_cast<uint32_t*>(rowp + x) = word;
+                    else { rowp[x] = (uint8_t)o0; if (x + 1 < dw) rowp[x + 1] = (uint8_t)o1; if (x + 2 < dw) rowp[x + 2] = (uint8_t)o2; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = x + k;
+                    if (c < dw) {
+                        const uint8_t px = (uint8_t)(word >> (8 * k));
+                        if (c >= 1 && c <= VO_BORDER) rowp[-c] = px;
+                        if (c >= dw - 1 - VO_BORDER && c <= dw - 2) rowp[2 * (dw - 1) - c] = px;
+                    }
+                }
+            };
+            put_row(y);
+            if (y >= 1 && y <= VO_BORDER) put_row(-y);
+            if (y >= dh - 1 - VO_BORDER && y <= dh - 2) put_row(2 * (dh - 1) - y);
+        }
     }
 }
 
@@ -282,11 +306,13 @@ int vo_build_pyramids(b200vo_ctx* ctx, const uint8_t* d_raw, size_t raw_stride, 
         // TMA needs 16-byte aligned strides and base: slab strides are multiples of 256, pitches of 128
         const bool tma_ok = (slab_stride % 16 == 0 || batch == 1) && (reinterpret_cast<uintptr_t>(d_slab) % 256 == 0);
         for (int l = 1; l < g.levels; ++l) {
+            bool fused = false;
             if (tma_ok) {
                 CUtensorMap map;
                 VO_TRY(pyr_src_map(ctx, &map, d_slab, batch == 1 ? g.slab_bytes : slab_stride, batch, g, l - 1));
                 dim3 grid((g.w[l] + PD_TW - 1) / PD_TW, (g.h[l] + PD_TH - 1) / PD_TH, batch);
-                pyr_down_tma_kernel<<<grid, 256, 0, ctx->stream>>>(map, d_slab, slab_stride, g.off[l], g.w[l], g.h[l], g.pitch[l]);
+                fused = g.w[l] >= VO_BORDER + 2 && g.h[l] >= VO_BORDER + 2;   // single-bounce reflection: the tiles write the ring
+                pyr_down_tma_kernel<<<grid, 256, 0, ctx->stream>>>(map, d_slab, slab_stride, g.off[l], g.w[l], g.h[l], g.pitch[l], fused ? 1 : 0);
             } else {
                 dim3 block(32, 8);
                 int gxn = (g.w[l] + 2 * VO_BORDER + 3) / 4;
@@ -296,8 +322,8 @@ int vo_build_pyramids(b200vo_ctx* ctx, const uint8_t* d_raw, size_t raw_stride, 
                                                                   g.pitch[l]);
             }
             ctx->launches++;
-            if (tma_ok) {
-                // the next level's halo tiles read this level's border: fill it before descending
+            if (tma_ok && !fused) {
+                // the next level's halo tiles read this level's border: fill it before descending (tiny levels: multi-bounce)
                 BorderArgs ba{};
                 ba.levels = l + 1;
                 for (int k = 0; k <= l; ++k) { ba.w[k] = g.w[k]; ba.h[k] = g.h[k]; ba.pitch[k] = g.pitch[k]; ba.off[k] = g.off[k]; }
