@@ -54,6 +54,11 @@ class SequenceBatch:
         self.pnp_ok = self.pinned_empty((b,), np.uint8)
         self.inlier_mask = self.pinned_empty((b, L), np.uint8)
         self.n_inliers = self.pinned_empty((b,), np.int32)
+        # ctypes views of the reused result arrays, built once (step() is called thousands of times per second)
+        self._out_ptrs = (_p(self.lm_next, c_f32p), _p(self.lm_status, c_u8p), _p(self.cand_next, c_f32p), _p(self.cand_status, c_u8p),
+                          _p(self.pose, c_f64p), _p(self.pnp_ok, c_u8p), _p(self.inlier_mask, c_u8p), _p(self.n_inliers, c_i32p))
+        self._out_dict = dict(lm_next=self.lm_next, lm_status=self.lm_status, cand_next=self.cand_next, cand_status=self.cand_status,
+                              pose=self.pose, pnp_ok=self.pnp_ok, inlier_mask=self.inlier_mask, n_inliers=self.n_inliers)
 
     def close(self):
         if getattr(self, "h", None):
@@ -123,14 +128,9 @@ class SequenceBatch:
             assert n_cand is not None and n_cand.dtype == np.int32 and n_cand.shape == (b,)
         rc = self.ctx.lib.b200vo_batch_step(
             self.h, _p(frames, c_u8p) if frames is not None else None, _p(lm_pts, c_f32p), _p(lm_obj, c_f32p), _p(n_lm, c_i32p),
-            _p(cand_pts, c_f32p) if Cn > 0 else None, _p(n_cand, c_i32p) if Cn > 0 else None,
-            _p(self.lm_next, c_f32p), _p(self.lm_status, c_u8p), _p(self.cand_next, c_f32p),
-            _p(self.cand_status, c_u8p), _p(self.pose, c_f64p), _p(self.pnp_ok, c_u8p),
-            _p(self.inlier_mask, c_u8p), _p(self.n_inliers, c_i32p))
+            _p(cand_pts, c_f32p) if Cn > 0 else None, _p(n_cand, c_i32p) if Cn > 0 else None, *self._out_ptrs)
         self._chk(rc, "b200vo_batch_step")
-        return dict(lm_next=self.lm_next, lm_status=self.lm_status, cand_next=self.cand_next,
-                    cand_status=self.cand_status, pose=self.pose, pnp_ok=self.pnp_ok,
-                    inlier_mask=self.inlier_mask, n_inliers=self.n_inliers)
+        return self._out_dict
 
     def good_features(self, max_corners=1400, quality=0.1, min_dist=10.0):
         """cv2.goodFeaturesToTrack (reference :256) on the current frame of every sequence (the frames the last
