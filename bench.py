@@ -376,7 +376,7 @@ def main():
                 "algorithmic_bytes_per_launch": klt_bytes, "avg_launch_ms": klt_ms,
                 "stage_ms_per_step": {"pyramid": float(stage_ms[0]) / max(int(nprof[0]), 1), "klt_landmarks": klt_ms,
                                       "pnp_beside_klt_candidates": float(stage_ms[2]) / max(int(nprof[0]), 1)},
-                "note": "klt_kernel_v2 is instruction-issue bound (smsp issue active 78 %, profiles/r1k_klt_kernel_full.txt): integer bilinear taps from shared-memory-staged windows; DRAM traffic ~ the algorithmic bytes; see DESIGN.md"}
+                "note": "klt_kernel_v2 is instruction-issue bound (smsp issue active 82 %, profiles/r1p_klt_kernel_full.txt): integer bilinear taps from shared-memory-staged windows; DRAM traffic ~ the algorithmic bytes; see DESIGN.md"}
 
     # ---- extra (not the headline): Shi-Tomasi detection (reference :256, feature_adding runs it every frame) for the
     # whole batch on the resident frames ----
