@@ -185,7 +185,7 @@ def main():
     from monocular_visual_odometry_va4mr_b200 import workload
     opts = workload.REFERENCE_OPTIONS[args.shape]
     cfg_common = {
-        "workload": f"{args.batch} independent synthetic {args.shape}-shaped sequences per GPU (BASELINE config 5 = 64 x config 1), "
+        "workload": f"{args.batch} independent synthetic {args.shape}-shaped sequences per GPU (BASELINE.json configs[4] = 64 x the configs[0] sequence shape; SURVEY's C5 = 64 x C1), "
                     f"one new frame each per step: KLT {opts['win'][0]}x{opts['win'][1]} maxLevel {opts['max_level']} criteria {opts['criteria']} on "
                     f"~{args.landmarks} landmark + ~{args.candidates} candidate keypoints, P3P-RANSAC {opts['pnp_iters']} it / {opts['pnp_err']} px + EPnP",
         "shape": args.shape, "sequences_per_gpu": args.batch, "landmarks": args.landmarks, "candidates": args.candidates,
