@@ -13,7 +13,7 @@
 // 0.05 px) and status flags are identical.
 #include "internal.cuh"
 
-#define KLT_WARPS 8
+#define KLT_WARPS 4
 #define W_BITS 14
 
 struct KltArgs {

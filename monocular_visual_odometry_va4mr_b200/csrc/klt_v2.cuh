@@ -38,8 +38,8 @@ struct KV2 {
     static constexpr int B_DER = DS * DH * 4;             // per plane
     static constexpr int B_IWIN = ((IS * WH * 2 + 15) / 16) * 16;
     static constexpr int PER_WARP = 2 * B_PATCH + B_J + 2 * B_DER + B_IWIN;   // two patch buffers (prefetch)
-    // resident CTAs per SM the shared memory allows (227 KB, 8 warps per CTA): the register budget follows it
-    static constexpr int MIN_CTAS = (227 * 1024) / (8 * PER_WARP + 64 + 1024) >= 4 ? 4 : 3;
+    // resident warps per SM the shared memory allows (227 KB): 32 (64 registers) or 24 (80); the register budget follows it
+    static constexpr int MIN_CTAS = ((227 * 1024) / (KLT_WARPS * PER_WARP + 64 + 1024) * KLT_WARPS >= 32 ? 32 : 24) / KLT_WARPS;
 };
 
 // 16-bit weights x 8-bit pixels.  The weights are SIGNED halves: iw11 = 2^14 - iw00 - iw01 - iw10 is -1
