@@ -52,7 +52,6 @@ def triangulate_landmarks(K, options, potential_first_keys, potential_keys, pote
     Returns ``(too_short_baseline bool (n,), new_landmarks float32 (k,3), new_keypoints float32 (k,2))``:
     the mask the reference passes to ``filter_potential`` (:206) and the rows it appends to
     ``matched_landmarks`` / ``matched_keypoints`` (:196-202)."""
-    ctx = ctx or _lib.default_context(0)
     fk = np.ascontiguousarray(potential_first_keys, np.float32).reshape(-1, 2)
     k = np.ascontiguousarray(potential_keys, np.float32).reshape(-1, 2)
     fp = np.ascontiguousarray(np.asarray(potential_transforms).reshape(-1), np.int32)
@@ -63,6 +62,7 @@ def triangulate_landmarks(K, options, potential_first_keys, potential_keys, pote
     n = len(k)
     if len(fk) != n or len(fp) != n:
         raise ValueError("potential_first_keys, potential_keys and potential_transforms must have one row per candidate")
+    ctx = ctx or _lib.default_context(0)
     keep = np.zeros(n, np.uint8)
     lm = np.zeros((max(n, 1), 3), np.float32)
     kp = np.zeros((max(n, 1), 2), np.float32)
