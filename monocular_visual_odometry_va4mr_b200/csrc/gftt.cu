@@ -322,26 +322,28 @@ gftt_candidates_kernel(const float* __restrict__ eig, int w, int h, const int* _
     n_keys += blockIdx.z * small_stride;
     keys += (size_t)blockIdx.z * cap;
     const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    bool is_c = false;
-    float v = 0.f;
-    if (x < w - 1 && y < h - 1) {
-        const float thr = (float)((double)__int_as_float(*max_bits) * quality);
-        const float* p = eig + (size_t)y * w + x;
-        v = p[0];
-        if (v > thr) {
-            is_c = !(p[-w - 1] > v || p[-w] > v || p[-w + 1] > v || p[-1] > v || p[1] > v || p[w - 1] > v || p[w] > v || p[w + 1] > v);
-        }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, is_c);
-    if (!m) return;
+    const float thr = (float)((double)__int_as_float(*max_bits) * quality);
     const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
-    int base = 0;
-    if (lane == __ffs(m) - 1) base = atomicAdd(n_keys, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (is_c) {
-        const int pos = base + __popc(m & ((1u << lane) - 1));
-        if (pos < cap) keys[pos] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                        // a 32 x 8 block covers 32 x 32 pixels: four rows per thread
+        const int y = blockIdx.y * 32 + 8 * k + threadIdx.y + 1;
+        bool is_c = false;
+        float v = 0.f;
+        if (x < w - 1 && y < h - 1) {
+            const float* p = eig + (size_t)y * w + x;
+            v = p[0];
+            if (v > thr)
+                is_c = !(p[-w - 1] > v || p[-w] > v || p[-w + 1] > v || p[-1] > v || p[1] > v || p[w - 1] > v || p[w] > v || p[w + 1] > v);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, is_c);
+        if (!m) continue;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(n_keys, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (is_c) {
+            const int pos = base + __popc(m & ((1u << lane) - 1));
+            if (pos < cap) keys[pos] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+        }
     }
 }
 
@@ -603,7 +605,7 @@ extern "C" int b200vo_good_features_to_track(b200vo_ctx* ctx, const uint8_t* img
         gftt_colsum_rs_kernel<<<(3 * w + 31) / 32, 32, 0, ctx->stream>>>(d_rs, w, h, d_box);
         gftt_eig_kernel<<<(int)((npx + 255) / 256), 256, 0, ctx->stream>>>(d_box, w, h, d_eig, d_small, 0);
         ctx->launches += 2;
-        dim3 grd2((w - 2 + 31) / 32, (h - 2 + 7) / 8);
+        dim3 grd2((w - 2 + 31) / 32, (h - 2 + 31) / 32);
         gftt_candidates_kernel<<<grd2, blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys, d_small + 1, cap, 0);
         ctx->launches += 3;
     }
@@ -694,7 +696,7 @@ int vo_gftt_batch_launch(b200vo_ctx* ctx, const uint8_t* d_img0, size_t img_stri
     dim3 blk(32, 8);
     gftt_fused_eig_kernel<<<dim3((w + GF_COLS - 1) / GF_COLS, batch), 32, 0, ctx->stream>>>(d_img0, img_stride, pitch, w, h, (float)scale,
                                                                                             (float)(2.0 * scale), d_eig, d_small, GFTT_SMALL);
-    gftt_candidates_kernel<<<dim3((w - 2 + 31) / 32, (h - 2 + 7) / 8, batch), blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys,
+    gftt_candidates_kernel<<<dim3((w - 2 + 31) / 32, (h - 2 + 31) / 32, batch), blk, 0, ctx->stream>>>(d_eig, w, h, d_small, quality, d_keys,
                                                                                                     d_small + 1, GFTT_BATCH_CAP, GFTT_SMALL);
     gftt_rank_kernel<<<dim3(GFTT_BATCH_CAP / 256, batch), 256, 0, ctx->stream>>>(d_keys, d_small + 1, GFTT_BATCH_CAP, d_sorted, GFTT_SMALL);
     if (cell_smem > 48 * 1024)
