@@ -567,15 +567,16 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
     }
     // chunks of hypotheses in stream order; a chunk whose first sample lies beyond cv2's adaptive
     // iteration bound (known on the device after the previous chunk) exits immediately
-    const int CH = 128;
     ctx->launches += 2;
     // every sample is solved up front: one warp each, so the launch is one wave of latency-bound warps
     // whether it carries 128 samples or all of them
     emat_solve_kernel<<<(iters + EMW_WARPS - 1) / EMW_WARPS, EMW_WARPS * 32, 0, ctx->stream>>>(a);
     ctx->launches += 1;
-    for (int c0 = 0; c0 < iters; c0 += CH) {
-        a.chunk_start = c0; a.chunk_len = CH;
-        emat_score_kernel<<<dim3((n + 255) / 256, (CH + EM_ST - 1) / EM_ST), 256, 0, ctx->stream>>>(a);
+    // scoring chunks of 64, 128, 256, ... samples: cv2 usually stops within the first (10-60 samples), and every
+    // chunk beyond the bound costs two empty launches
+    for (int c0 = 0, len = 64; c0 < iters; c0 += len, len *= 2) {
+        a.chunk_start = c0; a.chunk_len = len;
+        emat_score_kernel<<<dim3((n + 255) / 256, (len + EM_ST - 1) / EM_ST), 256, 0, ctx->stream>>>(a);
         emat_update_kernel<<<1, 32, 0, ctx->stream>>>(a);
         ctx->launches += 2;
     }
