@@ -12,7 +12,7 @@
 //   emat_score_kernel       (256 points) x (8 samples x <=10 models): Sampson error in double ->
 //                           float32, ballot+popc counts, one atomicAdd per warp
 //   emat_update_kernel      sequential replay of cv2's loop over (sample, model) counts with the
-//                           adaptive iteration bound; hypotheses go through in chunks of 128 and a
+//                           adaptive iteration bound; hypotheses go through in chunks of 64, 128, 256, ... and a
 //                           chunk beyond the bound exits at once (cv2 stops after 10-60 samples)
 //   emat_finish_kernel      the winner's E and mask
 #include "internal.cuh"
