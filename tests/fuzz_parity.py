@@ -8,7 +8,7 @@ sizes, maxLevel 0..6, all three criteria types, points on quarter-pixel grids an
 211 goodFeaturesToTrack, 210 knnMatch (with planted duplicate descriptors), 210 solvePnPRansac,
 210 findEssentialMat + recoverPose, 210 min-distance masks: 0 mismatches.  Seeds 2 and 3 (500 s, + 428
 triangulation loops): one findEssentialMat mask differing in ONE point (threshold tie, see below), nothing else.
-Seed 4 on the round-1 end state (330 s, 3 372 calls): 0 mismatches."""
+Seed 4 (330 s, 3 372 calls) and seed 6 on the final round-1 binary (300 s, 3 012 calls): 0 mismatches."""
 import os
 import sys
 import time
