@@ -21,6 +21,34 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
+class _PinnedBlock:
+    """Owner of one b200vo_host_alloc block.  The numpy arrays carved from it keep it alive (it hangs off the
+    ctypes buffer that is the arrays' base), so a result array that outlives its SequenceBatch -- e.g.
+    ``SequenceBatch(...).step(...)['pose']`` -- never points into freed page-locked memory: the block is
+    released when the LAST array referring to it is collected."""
+
+    def __init__(self, ctx: _lib.Context, nbytes: int):
+        self.ctx, self.nbytes = ctx, nbytes
+        self.ptr = ctx.lib.b200vo_host_alloc(ctx.h, nbytes)
+        if not self.ptr:
+            raise MemoryError("b200vo_host_alloc")
+
+    def array(self, shape, dtype) -> np.ndarray:
+        dt = np.dtype(dtype)
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        buf._owner = self          # ndarray.base -> memoryview -> buf -> this block
+        return np.frombuffer(buf, dt, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                # the context may already be closed: page-locked memory is freed all the same (ctx == NULL)
+                self.ctx.lib.b200vo_host_free(self.ctx.h if getattr(self.ctx, "h", None) else None, self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 class SequenceBatch:
     def __init__(self, batch, rows, cols, K, win=(15, 15), max_level=5, criteria=(3, 50, 0.01),
                  min_eig_thr=1e-4, pnp_iters=500, pnp_reproj_err=8.0, pnp_conf=0.99,
@@ -61,12 +89,12 @@ class SequenceBatch:
                               pose=self.pose, pnp_ok=self.pnp_ok, inlier_mask=self.inlier_mask, n_inliers=self.n_inliers)
 
     def close(self):
+        """Destroys the device-side batch.  Page-locked arrays handed out by this object (step() results,
+        pinned_empty / pinned_like / pinned_frames) stay valid for as long as they are referenced: each block is
+        owned by its arrays (_PinnedBlock) and released with the last of them."""
         if getattr(self, "h", None):
             self.ctx.lib.b200vo_batch_destroy(self.h)
             self.h = None
-            for ptr in getattr(self, "_pinned", []):
-                self.ctx.lib.b200vo_host_free(self.ctx.h, ptr)
-            self._pinned = []
 
     def __del__(self):
         try:
@@ -82,12 +110,7 @@ class SequenceBatch:
         """numpy array in page-locked host memory (b200vo_host_alloc): DMA'd in place by step()."""
         dt = np.dtype(dtype)
         nbytes = max(int(np.prod(shape)) * dt.itemsize, 1)
-        ptr = self.ctx.lib.b200vo_host_alloc(self.ctx.h, nbytes)
-        if not ptr:
-            raise MemoryError("b200vo_host_alloc")
-        self._pinned = getattr(self, "_pinned", []) + [ptr]
-        buf = (C.c_uint8 * nbytes).from_address(ptr)
-        return np.frombuffer(buf, dt, count=int(np.prod(shape))).reshape(shape)
+        return _PinnedBlock(self.ctx, nbytes).array(shape, dt)
 
     def pinned_like(self, arr: np.ndarray) -> np.ndarray:
         out = self.pinned_empty(arr.shape, arr.dtype)
@@ -96,14 +119,7 @@ class SequenceBatch:
 
     def pinned_frames(self, n_sets: int = 1) -> np.ndarray:
         """(n_sets, batch, rows, cols) uint8 array in page-locked memory (b200vo_host_alloc)."""
-        nbytes = n_sets * self.batch * self.rows * self.cols
-        ptr = self.ctx.lib.b200vo_host_alloc(self.ctx.h, nbytes)
-        if not ptr:
-            raise MemoryError("b200vo_host_alloc")
-        buf = (C.c_uint8 * nbytes).from_address(ptr)
-        arr = np.frombuffer(buf, np.uint8).reshape(n_sets, self.batch, self.rows, self.cols)
-        self._pinned = getattr(self, "_pinned", []) + [ptr]
-        return arr
+        return self.pinned_empty((n_sets, self.batch, self.rows, self.cols), np.uint8)
 
     def prime(self, frames: np.ndarray):
         frames = np.ascontiguousarray(frames, np.uint8).reshape(self.batch, self.rows, self.cols)
@@ -116,16 +132,21 @@ class SequenceBatch:
         self._chk(self.ctx.lib.b200vo_batch_submit_frames(self.h, _p(frames, c_u8p)), "b200vo_batch_submit_frames")
 
     def step(self, frames, lm_pts, lm_obj, n_lm, cand_pts=None, n_cand=None):
-        """Host buffers in, host buffers out (synchronous).  Returns a dict of views on reused arrays.
+        """Host buffers in, host buffers out (synchronous).  Returns a dict of views on REUSED page-locked arrays:
+        the next step() overwrites them (copy what must survive it); they remain valid memory after close().
         frames=None: use the oldest frame set given to submit_frames()."""
         b, L, Cn = self.batch, self.L, self.Cn
         assert frames is None or (frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.size == b * self.rows * self.cols)
         assert lm_pts.dtype == np.float32 and lm_pts.shape == (b, L, 2) and lm_pts.flags.c_contiguous
         assert lm_obj.dtype == np.float32 and lm_obj.shape == (b, L, 3) and lm_obj.flags.c_contiguous
         assert n_lm.dtype == np.int32 and n_lm.shape == (b,)
+        if n_lm.min() < 0 or n_lm.max() > L:
+            raise ValueError(f"n_lm must lie in [0, max_landmarks = {L}]")
         if Cn > 0:
             assert cand_pts is not None and cand_pts.dtype == np.float32 and cand_pts.shape == (b, Cn, 2)
             assert n_cand is not None and n_cand.dtype == np.int32 and n_cand.shape == (b,)
+            if n_cand.min() < 0 or n_cand.max() > Cn:
+                raise ValueError(f"n_cand must lie in [0, max_candidates = {Cn}]")
         rc = self.ctx.lib.b200vo_batch_step(
             self.h, _p(frames, c_u8p) if frames is not None else None, _p(lm_pts, c_f32p), _p(lm_obj, c_f32p), _p(n_lm, c_i32p),
             _p(cand_pts, c_f32p) if Cn > 0 else None, _p(n_cand, c_i32p) if Cn > 0 else None, *self._out_ptrs)

@@ -40,8 +40,8 @@ struct b200vo_batch {
     bool primed;
     // host-input path: frames arrive chunk by chunk on a copy stream while earlier chunks are tracked
     cudaStream_t chunk_stream[B200VO_BATCH_STREAMS] = {};  // chunk k: H2D -> pyramid -> KLT on stream k % STREAMS
-    cudaEvent_t chunk_ev[B200VO_BATCH_CHUNKS];
-    cudaEvent_t copy_ev[B200VO_BATCH_CHUNKS];   // chunk k's frames have landed (copies run back to back on pre_stream)
+    cudaEvent_t chunk_ev[B200VO_BATCH_CHUNKS] = {};
+    cudaEvent_t copy_ev[B200VO_BATCH_CHUNKS] = {};   // chunk k's frames have landed (copies run back to back on pre_stream)
     cudaEvent_t done_ev = nullptr;
     cudaStream_t io_stream = nullptr;      // landmark upload / KLT result read-back beside the kernels
     // PnP is a chain of small latency-bound kernels that needs the LANDMARK tracks only: it runs on a
@@ -52,6 +52,7 @@ struct b200vo_batch {
     // optional per-kernel timing (CUDA events on the ctx stream): [step][stage] boundaries
     bool profile = false;
     int prof_n = 0;
+    bool prof_row_open = false;   // marks 0 and 1 of row prof_n were recorded by this step
     cudaEvent_t prof_ev[B200VO_PROF_RING][B200VO_PROF_STAGES + 1];
     bool prof_init = false;
 };
@@ -73,7 +74,7 @@ compact_tracked_kernel(int cap, const int* __restrict__ n_lm, const float* __res
     __shared__ int s_warp[8];
     __shared__ int s_base;
     const int b = blockIdx.x;
-    const int n = n_lm[b];
+    const int n = min(max(n_lm[b], 0), cap);   // a count beyond the slot capacity must not reach the neighbour's arrays
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
@@ -149,24 +150,28 @@ extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batc
     B->n_raw = 8 * cfg->pnp_iters + 256;
     if (!rc) rc = vo_rng_table(ctx, B->n_raw, &B->rng);
     if (rc) { b200vo_batch_destroy(B); return rc; }
-    cudaStreamCreateWithFlags(&B->pre_stream, cudaStreamNonBlocking);
-    {   // chunk streams carry pyramids + the landmark tracker: ahead of the candidate tracker on the ctx stream
+    {   // streams and events: any failure (descriptor / memory exhaustion with many batches) unwinds the whole object
+        cudaError_t ce = cudaSuccess;
+        auto ok = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; };
         int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        for (auto& st : B->chunk_stream) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest);
+        ok(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        ok(cudaStreamCreateWithFlags(&B->pre_stream, cudaStreamNonBlocking));
+        // chunk streams carry pyramids + the landmark tracker: ahead of the candidate tracker on the ctx stream
+        for (auto& st : B->chunk_stream) ok(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest));
+        for (auto& e : B->chunk_ev) ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : B->copy_ev) ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&B->done_ev, cudaEventDisableTiming));
+        ok(cudaStreamCreateWithFlags(&B->io_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&B->obj_ev, &B->klt_ev, &B->io_ev, &B->lm_ev, &B->cand_ev, &B->pose_ev})
+            ok(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        ok(cudaStreamCreateWithPriority(&B->pose_stream, cudaStreamNonBlocking, greatest));
+        for (auto& e : B->q_ev) ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&B->step_end_ev, cudaEventDisableTiming));
+        if (ce != cudaSuccess) {
+            b200vo_batch_destroy(B);
+            return vo_cuda_fail(ctx, ce, "b200vo_batch_create: stream / event creation");
+        }
     }
-    for (auto& e : B->chunk_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    for (auto& e : B->copy_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&B->done_ev, cudaEventDisableTiming);
-    cudaStreamCreateWithFlags(&B->io_stream, cudaStreamNonBlocking);
-    for (cudaEvent_t* e : {&B->obj_ev, &B->klt_ev, &B->io_ev, &B->lm_ev, &B->cand_ev, &B->pose_ev}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
-    {
-        int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        cudaStreamCreateWithPriority(&B->pose_stream, cudaStreamNonBlocking, greatest);
-    }
-    for (auto& e : B->q_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&B->step_end_ev, cudaEventDisableTiming);
     uint8_t* p = (uint8_t*)B->work.p;
     B->c_obj = (float*)p; p += b_obj;
     B->c_img = (float*)p; p += b_img;
@@ -184,23 +189,20 @@ extern "C" void b200vo_batch_destroy(b200vo_batch* B)
     if (!B) return;
     cudaSetDevice(B->ctx->device);
     cudaStreamSynchronize(B->ctx->stream);
+    auto kill_stream = [](cudaStream_t st) { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } };
+    auto kill_event = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
+    kill_stream(B->pre_stream);
+    for (auto& st : B->chunk_stream) kill_stream(st);
+    kill_stream(B->io_stream);
+    kill_stream(B->pose_stream);
     for (auto& s : B->slabs) if (s.p) cudaFree(s.p);
-    if (B->pre_stream) {
-        cudaStreamSynchronize(B->pre_stream); cudaStreamDestroy(B->pre_stream);
-        for (auto& e : B->q_ev) cudaEventDestroy(e);
-        cudaEventDestroy(B->step_end_ev);
-    }
     for (DevBuf* d : {&B->raw, &B->raw_pre, &B->pts_in, &B->outs, &B->work, &B->gftt_ws}) if (d->p) cudaFree(d->p);
-    if (B->prof_init) for (auto& row : B->prof_ev) for (auto& e : row) cudaEventDestroy(e);
-    if (B->chunk_stream[0]) {
-        for (auto& st : B->chunk_stream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-        for (auto& e : B->chunk_ev) cudaEventDestroy(e);
-        for (auto& e : B->copy_ev) cudaEventDestroy(e);
-        cudaEventDestroy(B->done_ev);
-        cudaStreamSynchronize(B->io_stream); cudaStreamDestroy(B->io_stream);
-        for (cudaEvent_t e : {B->obj_ev, B->klt_ev, B->io_ev, B->lm_ev, B->cand_ev, B->pose_ev}) cudaEventDestroy(e);
-        cudaStreamSynchronize(B->pose_stream); cudaStreamDestroy(B->pose_stream);
-    }
+    for (auto& e : B->q_ev) kill_event(e);
+    for (auto& e : B->chunk_ev) kill_event(e);
+    for (auto& e : B->copy_ev) kill_event(e);
+    for (cudaEvent_t e : {B->step_end_ev, B->done_ev, B->obj_ev, B->klt_ev, B->io_ev, B->lm_ev, B->cand_ev, B->pose_ev}) kill_event(e);
+    if (B->prof_init) for (auto& row : B->prof_ev) for (auto& e : row) kill_event(e);
+    cudaGetLastError();
     delete B;
 }
 
@@ -316,11 +318,12 @@ static int batch_track(b200vo_batch* B, int b0, int nb, const uint8_t* frames_de
     const size_t fb = (size_t)c.rows * c.cols, sb = B->geom.slab_bytes;
     const int L = c.max_landmarks, Cn = c.max_candidates;
     if (which == 0 || which == 3 || which == 4) {
-        if (b0 == 0) prof_mark(B, 0);
+        const bool whole = b0 == 0 && nb == B->batch;   // chunked uploads build the pyramids piecewise: no single interval to time
+        if (whole) prof_mark(B, 0);
         if (frames_dev)
             VO_TRY(vo_build_pyramids(ctx, frames_dev + (size_t)b0 * fb, fb, c.rows, c.cols, B->geom,
                                      (uint8_t*)B->slabs[nxt].p + (size_t)b0 * sb, sb, nb));
-        if (b0 == 0 && nb == B->batch) prof_mark(B, 1);
+        if (whole) { prof_mark(B, 1); B->prof_row_open = B->profile && B->prof_n < B200VO_PROF_RING; }
     }
     KltPointSet sets[2] = {{L, n_lm + b0, lm_pts + (size_t)b0 * L * 2, lm_next + (size_t)b0 * L * 2, lm_status + (size_t)b0 * L, nullptr},
                            {Cn, n_cand + b0, cand_pts + (size_t)b0 * Cn * 2, cand_next + (size_t)b0 * Cn * 2,
@@ -339,7 +342,7 @@ static int batch_pose(b200vo_batch* B, const float* lm_obj, const int* n_lm, con
 {
     b200vo_ctx* ctx = B->ctx;
     const b200vo_batch_cfg& c = B->cfg;
-    prof_mark(B, 2);
+    if (B->prof_row_open) prof_mark(B, 2);
     compact_tracked_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, n_lm, lm_next, lm_status, lm_obj,
                                                               B->c_obj, B->c_img, B->c_n, B->c_orig);
     ctx->launches++;
@@ -357,8 +360,7 @@ static int batch_pose(b200vo_batch* B, const float* lm_obj, const int* n_lm, con
     scatter_mask_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, a.ok, a.n_inliers, B->inliers, B->c_orig,
                                                            inlier_mask, n_inliers, pnp_ok);
     ctx->launches++;
-    prof_mark(B, 3);
-    if (B->profile && B->prof_n < B200VO_PROF_RING) B->prof_n++;
+    if (B->prof_row_open) { prof_mark(B, 3); B->prof_n++; B->prof_row_open = false; }
     VO_CUDA(ctx, cudaGetLastError());
     return 0;
 }
@@ -410,7 +412,11 @@ static int batch_core(b200vo_batch* B, const uint8_t* frames_dev, const float* l
 {
     if (!B->primed) return vo_set_err(B->ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
     if (!frames_dev) return vo_set_err(B->ctx, B200VO_E_BADARG, "null pointer");
-    B->nxt = batch_free_set(B);
+    if (B->q_count > 0)
+        return vo_set_err(B->ctx, B200VO_E_BADARG, "submitted frame sets are waiting: consume them with b200vo_batch_step(frames == NULL) first");
+    const int free_set = batch_free_set(B);
+    if (free_set < 0) return vo_set_err(B->ctx, B200VO_E_BADARG, "no free pyramid set");
+    B->nxt = free_set;
     VO_TRY(batch_track_pose_overlapped(B, frames_dev, lm_pts, lm_obj, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next,
                                        cand_status, pose, pnp_ok, inlier_mask, n_inliers, nullptr));
     return batch_finish(B);
@@ -459,6 +465,12 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
         if (B->outs.p != before) VO_CUDA(ctx, cudaMemsetAsync(B->outs.p, 0, out_bytes, ctx->stream));
     }
     if (!B->primed) return vo_set_err(ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
+    for (int b = 0; b < nb; ++b) {   // the counts are host arrays here: a count beyond the slot capacity is a caller bug
+        if (n_lm[b] < 0 || n_lm[b] > L)
+            return vo_set_err(ctx, B200VO_E_BADARG, "n_lm[%d] = %d is outside [0, max_landmarks = %d]", b, n_lm[b], L);
+        if (Cn > 0 && cand_pts && n_cand && (n_cand[b] < 0 || n_cand[b] > Cn))
+            return vo_set_err(ctx, B200VO_E_BADARG, "n_cand[%d] = %d is outside [0, max_candidates = %d]", b, n_cand[b], Cn);
+    }
     const bool prefetched = frames == nullptr;
     if (prefetched && B->q_count == 0)
         return vo_set_err(ctx, B200VO_E_BADARG, "frames == NULL but no frame set was submitted (b200vo_batch_submit_frames)");
@@ -479,6 +491,7 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
         B->q_count--;
     } else {
         B->nxt = batch_free_set(B);
+        if (B->nxt < 0) return vo_set_err(ctx, B200VO_E_BADARG, "no free pyramid set");
     }
     // Sequences are processed in chunks, each on its own stream: H2D of its frames -> pyramids -> KLT.
     // The copies queue on the DMA engine in order, so chunk k+1 is on the wire while chunk k is tracked,
@@ -658,6 +671,8 @@ extern "C" int b200vo_batch_profile(b200vo_batch* B, int enable)
     }
     B->profile = enable != 0;
     B->prof_n = 0;
+    B->prof_row_open = false;
+    cudaGetLastError();
     return 0;
 }
 
@@ -667,13 +682,18 @@ extern "C" int b200vo_batch_profile_read(b200vo_batch* B, float* stage_ms, int* 
     cudaSetDevice(B->ctx->device);
     cudaStreamSynchronize(B->ctx->stream);
     for (int s = 0; s < B200VO_PROF_STAGES; ++s) stage_ms[s] = 0.f;
-    for (int i = 0; i < B->prof_n; ++i)
-        for (int s = 0; s < B200VO_PROF_STAGES; ++s) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, B->prof_ev[i][s], B->prof_ev[i][s + 1]);
-            stage_ms[s] += ms;
-        }
-    *n_steps = B->prof_n;
+    for (cudaStream_t st : {B->pose_stream, B->pre_stream}) if (st) cudaStreamSynchronize(st);
+    int rows = 0;
+    for (int i = 0; i < B->prof_n; ++i) {
+        float ms[B200VO_PROF_STAGES];
+        bool ok = true;
+        for (int s = 0; s < B200VO_PROF_STAGES && ok; ++s)
+            ok = cudaEventElapsedTime(&ms[s], B->prof_ev[i][s], B->prof_ev[i][s + 1]) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); continue; }   // an incomplete row must not leave a sticky error behind
+        for (int s = 0; s < B200VO_PROF_STAGES; ++s) stage_ms[s] += ms[s];
+        rows++;
+    }
+    *n_steps = rows;
     return 0;
 }
 
@@ -688,7 +708,7 @@ extern "C" void* b200vo_host_alloc(b200vo_ctx* ctx, size_t bytes)
 
 extern "C" void b200vo_host_free(b200vo_ctx* ctx, void* p)
 {
-    if (!ctx || !p) return;
-    cudaSetDevice(ctx->device);
+    if (!p) return;
+    if (ctx) cudaSetDevice(ctx->device);   // ctx == NULL: the context is already gone; page-locked memory is freed all the same
     cudaFreeHost(p);
 }

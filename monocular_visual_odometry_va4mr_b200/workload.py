@@ -25,10 +25,19 @@ REFERENCE_OPTIONS = {
 }
 
 
+def frame_at(n_frames: int, t: int) -> int:
+    """Frame index visited at step t >= 0 (forwards, then backwards, ...): defined for EVERY t, so loops
+    that look one or two steps ahead never run off the end of a precomputed list."""
+    if n_frames <= 1:
+        return 0
+    period = 2 * n_frames - 2
+    k = t % period
+    return k if k < n_frames else period - k
+
+
 def frame_order(n_frames: int, n_steps: int) -> list[int]:
     """Frame index visited at step t = 0..n_steps (forwards, then backwards, ...)."""
-    period = list(range(n_frames)) + list(range(n_frames - 2, 0, -1))
-    return [period[t % len(period)] for t in range(n_steps + 1)]
+    return [frame_at(n_frames, t) for t in range(n_steps + 1)]
 
 
 class TrackWorkload:
@@ -36,7 +45,10 @@ class TrackWorkload:
 
     def __init__(self, shape="kitti", batch=64, n_frames=4, n_landmarks=1000, n_candidates=1000, n_distinct=2,
                  seed=0, outlier_frac=0.1, noise_px=0.3, width=None, height=None, cap_landmarks=None,
-                 cap_candidates=None):
+                 cap_candidates=None, first_index=None):
+        """first_index: global index of this workload's first sequence.  When given, sequence g = first_index + s
+        uses scene g % n_distinct and its own random stream, so the sequence is the same however the batch is
+        sharded over ranks (contiguous blocks of sequences per GPU)."""
         K, w, h, step, _ = synth.SHAPES[shape]
         self.shape, self.K = shape, K.copy()
         self.w, self.h = width or w, height or h
@@ -44,9 +56,16 @@ class TrackWorkload:
         self.L = cap_landmarks or n_landmarks
         self.Cn = cap_candidates if cap_candidates is not None else n_candidates
         rng = np.random.default_rng(seed)
-        seqs = [synth.render_sequence(shape, n_frames, seed=seed * 131 + d, width=self.w, height=self.h)
-                for d in range(n_distinct)]
+        g0 = first_index or 0
+        used = sorted({(g0 + s) % n_distinct for s in range(batch)})
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        with ThreadPoolExecutor(max_workers=min(len(used), os.cpu_count() or 1)) as pool:
+            rendered = list(pool.map(lambda d: synth.render_sequence(shape, n_frames, seed=seed * 131 + d, width=self.w,
+                                                                     height=self.h), used))
+        seqs = dict(zip(used, rendered))
         self.seqs = seqs
+        self.n_distinct, self.first_index = n_distinct, g0
         self.frames = np.empty((n_frames, batch, self.h, self.w), np.uint8)
         self.lm_pts = np.zeros((n_frames, batch, self.L, 2), np.float32)
         self.lm_obj = np.zeros((n_frames, batch, self.L, 3), np.float32)
@@ -54,17 +73,19 @@ class TrackWorkload:
         self.cand_pts = np.zeros((n_frames, batch, max(self.Cn, 1), 2), np.float32)
         self.n_cand = np.zeros((n_frames, batch), np.int32)
         pool = {}
-        for d in range(n_distinct):
+        for d in used:
             for f in range(n_frames):
                 pool[d, f] = synth.grid_corners(seqs[d]["frames"][f], 2 * (n_landmarks + n_candidates), seed=seed + 7 * d + f)
         for s in range(batch):
-            d = s % n_distinct
+            d = (g0 + s) % n_distinct
             sq = seqs[d]
+            if first_index is not None:
+                rng = np.random.default_rng([seed, g0 + s])
             for f in range(n_frames):
                 self.frames[f, s] = sq["frames"][f]
                 pts = pool[d, f][rng.permutation(len(pool[d, f]))]
-                nl = min(self.L, n_landmarks - (s % 5) * 7)          # ragged live counts
-                nc = min(self.Cn, n_candidates - (s % 3) * 11) if self.Cn else 0
+                nl = min(self.L, max(4, n_landmarks - ((g0 + s) % 5) * 7))          # ragged live counts
+                nc = min(self.Cn, max(0, n_candidates - ((g0 + s) % 3) * 11)) if self.Cn else 0
                 # the reference only keeps landmarks within [min_dist, max_dist] of the camera
                 # (main.py:22-23 ...; VisualOdometryPipeLine.py:168): landmarks come from that depth band
                 zi = sq["depth"][f][np.clip(np.rint(pts[:, 1]).astype(int), 0, self.h - 1),
@@ -97,6 +118,6 @@ class TrackWorkload:
 
     def true_pose(self, s: int, f: int):
         """World->camera (R, t) of frame f of sequence s (what solvePnPRansac should recover)."""
-        sq = self.seqs[s % len(self.seqs)]
+        sq = self.seqs[(self.first_index + s) % self.n_distinct]
         R_cw, c = sq["R_cw"][f], sq["c"][f]
         return R_cw.T, -R_cw.T @ c
