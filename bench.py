@@ -57,6 +57,7 @@ def parse(argv=None):
     ap.add_argument("--no-single", action="store_true", help="skip the extra one-sequence-per-call and detection measurements")
     ap.add_argument("--no-weak", action="store_true", help="skip the extra 64-per-GPU (weak scaling) measurement at N > 1")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run oracle check of the last timed step")
+    ap.add_argument("--no-lookahead", action="store_true", help="device-resident loop: pass each step's frames with the step instead of one step ahead")
     return ap.parse_args(argv)
 
 
@@ -293,11 +294,18 @@ class Arm:
                      inlier_mask=torch.zeros((b, L), dtype=torch.uint8, device=dev), n_inliers=torch.zeros((b,), dtype=torch.int32, device=dev))
         torch.cuda.synchronize()
 
+        ahead = not self.args.no_lookahead
+
         def dev_step(t):
+            # look-ahead form (default): the frames of step t+1 were handed over one step earlier
+            # (b200vo_batch_submit_frames_dev), so their pyramids are built beside step t-1's pose chain -- what the
+            # streaming host API does with b200vo_batch_submit_frames; every input is resident in HBM either way
             f, g = self.fo(t), self.fo(t + 1)
             o = {k: v.data_ptr() for k, v in d_out.items()}
             o["pose"] = d_out["pose"][t].data_ptr()
-            sb.step_dev(d_frames[g].data_ptr(), d_lm_pts[f].data_ptr(), d_lm_obj[f].data_ptr(), d_n_lm[f].data_ptr(),
+            if ahead:
+                sb.submit_frames_dev(d_frames[self.fo(t + 2)].data_ptr())
+            sb.step_dev(None if ahead else d_frames[g].data_ptr(), d_lm_pts[f].data_ptr(), d_lm_obj[f].data_ptr(), d_n_lm[f].data_ptr(),
                         d_cand[f].data_ptr(), d_n_cand[f].data_ptr(), o)
 
         def gather():
@@ -309,6 +317,8 @@ class Arm:
             return g
 
         sb.prime(wl.frames[self.fo(0)])
+        if ahead:
+            sb.submit_frames_dev(d_frames[self.fo(1)].data_ptr())
         for t in range(W):
             dev_step(t)
         if self.world > 1:   # the gather of the timed region runs once untimed first (NCCL sets its channels up lazily)
@@ -678,6 +688,8 @@ def main(argv=None):
             "dtype": "i32/f32+f64", "data": "synthetic",
             "config": dict(cfg_common, sequences_per_gpu=counts, pyramid_levels=levels, pnp_ok_last_step=res["n_ok"],
                            distinct_scenes=args.distinct, gathered_sequences=res["gathered_sequences"],
+                           device_loop=("frames of step t+1 handed over one step ahead (b200vo_batch_submit_frames_dev), consumed by "
+                                        "b200vo_batch_step_dev(frames=NULL)" if not args.no_lookahead else "b200vo_batch_step_dev(frames)"),
                            parallelism=f"sequences sharded x{world} ({args.scaling} scaling), NCCL all_gather of poses"),
             "clocks": clocks,
             "e2e": e2e,

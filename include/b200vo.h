@@ -94,6 +94,18 @@ int b200vo_knn2_ratio(b200vo_ctx* ctx, const float* q, int nq, const float* t, i
 int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1, const float* p2, int n,
                                      const double K[9], double prob, double thr, int max_iters,
                                      double E[9], uint8_t* mask, int* found);
+/*
+ * The same RANSAC on the caller's hypothesis sample set (parity runs; the counterpart of
+ * b200vo_solve_pnp_ransac_p3p_samples): samples int32 (iters,5).  Every sample is solved and scored;
+ * nmodels_out int32 (iters) = models per sample (ascending-root order), counts_out int32 (iters,10) =
+ * inliers per (sample, model), models_out double (iters,10,3,3) or NULL, *winner_out = sample * 10 + model
+ * as cv2's sequential loop picks it (-1: none), *iters_run = iterations that loop executes.
+ */
+int b200vo_find_essential_mat_ransac_samples(b200vo_ctx* ctx, const float* p1, const float* p2, int n,
+                                             const double K[9], const int32_t* samples, int iters,
+                                             double prob, double thr, double E[9], uint8_t* mask,
+                                             int* found, int32_t* nmodels_out, int32_t* counts_out,
+                                             double* models_out, int* winner_out, int* iters_run);
 
 /*
  * ---- components next to the hot path ----
@@ -200,9 +212,13 @@ int b200vo_batch_step(b200vo_batch* b, const uint8_t* frames, const float* lm_pt
  * consumes them (b200vo_batch_step with frames == NULL) has returned.  At most two sets may wait.
  */
 int b200vo_batch_submit_frames(b200vo_batch* b, const uint8_t* frames);
+/* The same look-ahead for frames that are already resident and complete in device memory: no copy,
+ * the pyramids are built from frames_dev on the side stream beside the step in flight.  Consumed
+ * by b200vo_batch_step_dev (or b200vo_batch_step) with frames == NULL, oldest first. */
+int b200vo_batch_submit_frames_dev(b200vo_batch* b, const uint8_t* frames_dev);
 /* Same step with every input already resident in device memory and outputs left there
  * (bench.py `value`: no host<->device copies in the timed region).  Asynchronous on the
- * ctx stream; pair with b200vo_sync. */
+ * ctx stream; pair with b200vo_sync.  frames_dev == NULL consumes the oldest submitted frame set. */
 int b200vo_batch_step_dev(b200vo_batch* b, const uint8_t* frames_dev, const float* lm_pts_dev,
                           const float* lm_obj_dev, const int32_t* n_lm_dev,
                           const float* cand_pts_dev, const int32_t* n_cand_dev, float* lm_next_dev,

@@ -57,6 +57,9 @@ SIGNATURES = {
         C.c_void_p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_double, c_i32p, c_f32p, c_u8p]),
     "b200vo_find_essential_mat_ransac": (C.c_int, [
         C.c_void_p, c_f32p, c_f32p, C.c_int, c_f64p, C.c_double, C.c_double, C.c_int, c_f64p, c_u8p, c_intp]),
+    "b200vo_find_essential_mat_ransac_samples": (C.c_int, [
+        C.c_void_p, c_f32p, c_f32p, C.c_int, c_f64p, c_i32p, C.c_int, C.c_double, C.c_double, c_f64p, c_u8p, c_intp,
+        c_i32p, c_i32p, c_f64p, c_intp, c_intp]),
     "b200vo_recover_pose": (C.c_int, [C.c_void_p, c_f64p, c_f32p, c_f32p, C.c_int, c_f64p, C.c_double, c_f64p, c_f64p, c_u8p, c_intp]),
     "b200vo_min_distance_mask": (C.c_int, [C.c_void_p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_float, c_u8p]),
     "b200vo_triangulate_landmarks": (C.c_int, [
@@ -72,6 +75,7 @@ SIGNATURES = {
     "b200vo_batch_destroy": (None, [C.c_void_p]),
     "b200vo_batch_prime": (C.c_int, [C.c_void_p, c_u8p]),
     "b200vo_batch_submit_frames": (C.c_int, [C.c_void_p, c_u8p]),
+    "b200vo_batch_submit_frames_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200vo_batch_good_features": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, c_f32p, c_i32p]),
     "b200vo_batch_step": (C.c_int, [
         C.c_void_p, c_u8p, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p, c_f32p, c_u8p, c_f32p, c_u8p,

@@ -131,6 +131,11 @@ class SequenceBatch:
         assert frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.size == self.batch * self.rows * self.cols
         self._chk(self.ctx.lib.b200vo_batch_submit_frames(self.h, _p(frames, c_u8p)), "b200vo_batch_submit_frames")
 
+    def submit_frames_dev(self, frames_dev: int):
+        """The same look-ahead for frames already resident in device memory (int from tensor.data_ptr()): the
+        pyramids are built beside the step in flight; step_dev(frames_dev=None, ...) consumes them."""
+        self._chk(self.ctx.lib.b200vo_batch_submit_frames_dev(self.h, frames_dev), "b200vo_batch_submit_frames_dev")
+
     def step(self, frames, lm_pts, lm_obj, n_lm, cand_pts=None, n_cand=None):
         """Host buffers in, host buffers out (synchronous).  Returns a dict of views on REUSED page-locked arrays:
         the next step() overwrites them (copy what must survive it); they remain valid memory after close().
@@ -164,10 +169,11 @@ class SequenceBatch:
         return corners, n
 
     def step_dev(self, frames_dev, lm_pts_dev, lm_obj_dev, n_lm_dev, cand_pts_dev, n_cand_dev, out_dev: dict):
-        """Device pointers in/out (ints from tensor.data_ptr()); asynchronous on the ctx stream."""
+        """Device pointers in/out (ints from tensor.data_ptr()); asynchronous on the ctx stream.
+        frames_dev=None: use the oldest frame set given to submit_frames_dev() / submit_frames()."""
         o = out_dev
         rc = self.ctx.lib.b200vo_batch_step_dev(
-            self.h, frames_dev, lm_pts_dev, lm_obj_dev, n_lm_dev, cand_pts_dev, n_cand_dev,
+            self.h, frames_dev or None, lm_pts_dev, lm_obj_dev, n_lm_dev, cand_pts_dev, n_cand_dev,
             o["lm_next"], o["lm_status"], o["cand_next"], o["cand_status"], o["pose"], o["pnp_ok"],
             o["inlier_mask"], o["n_inliers"])
         self._chk(rc, "b200vo_batch_step_dev")

@@ -23,7 +23,8 @@ struct b200vo_batch {
     DevBuf slabs[3];         // [batch] pyramids each: previous frames, frames being tracked, frames prefetched
     // frames submitted ahead of their step (b200vo_batch_submit_frames): FIFO of at most two slab sets
     int q_set[2]; int q_head = 0, q_count = 0;
-    const uint8_t* q_src[2] = {};   // host frames whose copy has not been enqueued yet (see batch_issue_prefetch)
+    const uint8_t* q_src[2] = {};   // frames whose copy / pyramid build has not been enqueued yet (see batch_issue_prefetch)
+    bool q_dev[2] = {};             // q_src is device memory (b200vo_batch_submit_frames_dev): no copy, pyramids straight from it
     cudaEvent_t q_ev[2] = {};
     cudaStream_t pre_stream = nullptr;
     cudaEvent_t step_end_ev = nullptr;
@@ -240,7 +241,7 @@ static int batch_free_set(const b200vo_batch* B)
 
 // Frames of a FUTURE step: copied and turned into pyramids on a side stream while the current step's
 // kernels run; the step that passes frames == NULL consumes them (oldest first).
-extern "C" int b200vo_batch_submit_frames(b200vo_batch* B, const uint8_t* frames)
+static int batch_submit(b200vo_batch* B, const uint8_t* frames, bool dev)
 {
     if (!B || !frames) return B200VO_E_BADARG;
     b200vo_ctx* ctx = B->ctx;
@@ -250,17 +251,31 @@ extern "C" int b200vo_batch_submit_frames(b200vo_batch* B, const uint8_t* frames
     const int set = batch_free_set(B);
     if (set < 0) return vo_set_err(ctx, B200VO_E_BADARG, "no free pyramid set");
     const size_t fb = (size_t)B->cfg.rows * B->cfg.cols, total = fb * B->batch;
-    VO_TRY(vo_reserve(ctx, B->raw_pre, total));
     cudaPointerAttributes at{};
-    const bool pinned = cudaPointerGetAttributes(&at, frames) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    const bool known = cudaPointerGetAttributes(&at, frames) == cudaSuccess;
     cudaGetLastError();
-    if (!pinned) return vo_set_err(ctx, B200VO_E_BADARG, "submitted frames must live in page-locked memory (b200vo_host_alloc)");
+    if (dev) {
+        if (!known || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged))
+            return vo_set_err(ctx, B200VO_E_BADARG, "b200vo_batch_submit_frames_dev needs a device pointer");
+    } else {
+        VO_TRY(vo_reserve(ctx, B->raw_pre, total));
+        if (!known || at.type != cudaMemoryTypeHost)
+            return vo_set_err(ctx, B200VO_E_BADARG, "submitted frames must live in page-locked memory (b200vo_host_alloc)");
+    }
     const int slot = (B->q_head + B->q_count) & 1;
     B->q_set[slot] = set;
     B->q_src[slot] = frames;
+    B->q_dev[slot] = dev;
     B->q_count++;
     return 0;
 }
+
+extern "C" int b200vo_batch_submit_frames(b200vo_batch* B, const uint8_t* frames) { return batch_submit(B, frames, false); }
+
+// The same for frames that are already resident (and complete) in device memory: no copy, the pyramids are built from
+// the caller's buffer on the side stream while the step in flight runs; b200vo_batch_step_dev(frames_dev == NULL)
+// consumes them.  The buffer must stay untouched until that step has been enqueued.
+extern "C" int b200vo_batch_submit_frames_dev(b200vo_batch* B, const uint8_t* frames_dev) { return batch_submit(B, frames_dev, true); }
 
 // Enqueue the copies + pyramid builds of the submitted frame sets that are still waiting.  Called
 // from inside the next step and ordered (event `after`) behind that step's own small uploads: the
@@ -276,10 +291,14 @@ static int batch_issue_prefetch(b200vo_batch* B, cudaEvent_t after = nullptr)
         if (!B->q_src[slot]) continue;
         VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->step_end_ev, 0));   // readers of this set have retired
         if (after) VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, after, 0));  // and the step's own uploads have landed
-        VO_CUDA(ctx, cudaMemcpyAsync(B->raw_pre.p, B->q_src[slot], total, cudaMemcpyHostToDevice, B->pre_stream));
+        const uint8_t* raw = B->q_src[slot];
+        if (!B->q_dev[slot]) {
+            VO_CUDA(ctx, cudaMemcpyAsync(B->raw_pre.p, B->q_src[slot], total, cudaMemcpyHostToDevice, B->pre_stream));
+            raw = (const uint8_t*)B->raw_pre.p;
+        }
         cudaStream_t main_stream = ctx->stream;
         ctx->stream = B->pre_stream;
-        const int rc = vo_build_pyramids(ctx, (const uint8_t*)B->raw_pre.p, fb, B->cfg.rows, B->cfg.cols, B->geom,
+        const int rc = vo_build_pyramids(ctx, raw, fb, B->cfg.rows, B->cfg.cols, B->geom,
                                          (uint8_t*)B->slabs[B->q_set[slot]].p, B->geom.slab_bytes, B->batch);
         ctx->stream = main_stream;
         if (rc) return rc;
@@ -343,9 +362,6 @@ static int batch_pose(b200vo_batch* B, const float* lm_obj, const int* n_lm, con
     b200vo_ctx* ctx = B->ctx;
     const b200vo_batch_cfg& c = B->cfg;
     if (B->prof_row_open) prof_mark(B, 2);
-    compact_tracked_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, n_lm, lm_next, lm_status, lm_obj,
-                                                              B->c_obj, B->c_img, B->c_n, B->c_orig);
-    ctx->launches++;
     PnpArgs a{};
     a.batch = B->batch; a.cap = c.max_landmarks; a.iters = c.pnp_iters;
     a.obj = B->c_obj; a.img = B->c_img; a.n = B->c_n;
@@ -356,10 +372,21 @@ static int batch_pose(b200vo_batch* B, const float* lm_obj, const int* n_lm, con
     a.inliers = B->inliers; a.mask = B->c_mask; a.pose = pose;
     vo_pnp_carve_workspace(a, B->pnp_ws);
     a.ok = a.ok_ws;
-    VO_TRY(vo_pnp_launch(ctx, a, true));
-    scatter_mask_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, a.ok, a.n_inliers, B->inliers, B->c_orig,
-                                                           inlier_mask, n_inliers, pnp_ok);
-    ctx->launches++;
+    if (vo_pnp_fused_ok(a, true)) {
+        // compaction, RANSAC, EPnP and the mask over the original slots: one CTA per sequence, one launch
+        PoseBatchIO io;
+        io.n_lm = n_lm; io.lm_next = lm_next; io.lm_status = lm_status; io.lm_obj = lm_obj;
+        io.c_orig = B->c_orig; io.mask_out = inlier_mask; io.n_inl_out = n_inliers; io.ok_out = pnp_ok;
+        VO_TRY(vo_pnp_fused_launch(ctx, a, io));
+    } else {
+        compact_tracked_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, n_lm, lm_next, lm_status, lm_obj,
+                                                                  B->c_obj, B->c_img, B->c_n, B->c_orig);
+        ctx->launches++;
+        VO_TRY(vo_pnp_launch(ctx, a, true));
+        scatter_mask_kernel<<<B->batch, 256, 0, ctx->stream>>>(c.max_landmarks, a.ok, a.n_inliers, B->inliers, B->c_orig,
+                                                               inlier_mask, n_inliers, pnp_ok);
+        ctx->launches++;
+    }
     if (B->prof_row_open) { prof_mark(B, 3); B->prof_n++; B->prof_row_open = false; }
     VO_CUDA(ctx, cudaGetLastError());
     return 0;
@@ -398,6 +425,10 @@ static int batch_track_pose_overlapped(b200vo_batch* B, const uint8_t* frames_de
     ctx->stream = main_stream;
     if (rc) return rc < 0 ? rc : vo_cuda_fail(ctx, (cudaError_t)rc, "pose stream");
     VO_CUDA(ctx, cudaEventRecord(B->pose_ev, B->pose_stream));
+    // The tracker is a persistent kernel (one grid fills every SM until its queue is empty): launched beside the
+    // landmark set, the candidate set would hold half the machine and the landmark tracks -- which the pose chain
+    // waits for -- would take twice as long.  So: landmark set alone, then candidate set and pose chain side by side.
+    VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->lm_ev, 0));
     VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status, 2));
     VO_CUDA(ctx, cudaEventRecord(B->cand_ev, main_stream));
     VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->pose_ev, 0));
@@ -410,13 +441,26 @@ static int batch_core(b200vo_batch* B, const uint8_t* frames_dev, const float* l
                       uint8_t* lm_status, float* cand_next, uint8_t* cand_status, double* pose, uint8_t* pnp_ok,
                       uint8_t* inlier_mask, int* n_inliers)
 {
-    if (!B->primed) return vo_set_err(B->ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
-    if (!frames_dev) return vo_set_err(B->ctx, B200VO_E_BADARG, "null pointer");
-    if (B->q_count > 0)
-        return vo_set_err(B->ctx, B200VO_E_BADARG, "submitted frame sets are waiting: consume them with b200vo_batch_step(frames == NULL) first");
-    const int free_set = batch_free_set(B);
-    if (free_set < 0) return vo_set_err(B->ctx, B200VO_E_BADARG, "no free pyramid set");
-    B->nxt = free_set;
+    b200vo_ctx* ctx = B->ctx;
+    if (!B->primed) return vo_set_err(ctx, B200VO_E_BADARG, "b200vo_batch_prime was not called");
+    if (!frames_dev) {
+        // the frames were handed over by b200vo_batch_submit_frames(_dev): their pyramids were (or are being) built on
+        // the side stream, beside the previous step
+        if (B->q_count == 0)
+            return vo_set_err(ctx, B200VO_E_BADARG, "frames == NULL but no frame set was submitted (b200vo_batch_submit_frames[_dev])");
+        const int q_slot = B->q_head;
+        VO_TRY(batch_issue_prefetch(B));                     // whatever is still waiting, this step's set first
+        B->nxt = B->q_set[q_slot];
+        B->q_head ^= 1;
+        B->q_count--;
+        VO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B->q_ev[q_slot], 0));
+    } else {
+        if (B->q_count > 0)
+            return vo_set_err(ctx, B200VO_E_BADARG, "submitted frame sets are waiting: pass frames == NULL to consume them in order");
+        const int free_set = batch_free_set(B);
+        if (free_set < 0) return vo_set_err(ctx, B200VO_E_BADARG, "no free pyramid set");
+        B->nxt = free_set;
+    }
     VO_TRY(batch_track_pose_overlapped(B, frames_dev, lm_pts, lm_obj, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next,
                                        cand_status, pose, pnp_ok, inlier_mask, n_inliers, nullptr));
     return batch_finish(B);

@@ -400,6 +400,7 @@ struct EmatArgs {
     double* E; uint8_t* mask; int* result; // result[0] = found, [1] = iterations run, [2] = winner flat index
     int* state;                            // [0] current iteration bound (niters), [1] max_good, [2] winner, [3] iterations replayed
     int chunk_start, chunk_len;
+    int full;                              // 1: score every sample (the caller reads counts[]); the replay still honours the bound
 };
 
 __global__ void __launch_bounds__(256)
@@ -448,7 +449,7 @@ emat_score_kernel(EmatArgs a)
 {
     __shared__ double s_E[EM_ST * EM_MAXM * 9];
     __shared__ int s_nm[EM_ST];
-    if (a.chunk_start >= a.state[0]) return;
+    if (!a.full && a.chunk_start >= a.state[0]) return;
     const int it0 = a.chunk_start + blockIdx.y * EM_ST;
     const int ns = min(EM_ST, min(a.iters, a.chunk_start + a.chunk_len) - it0);
     if (ns <= 0) return;
@@ -512,8 +513,9 @@ emat_finish_kernel(EmatArgs a)
 
 int vo_rng_table(b200vo_ctx* ctx, int n, const uint32_t** d_table);
 
-extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1, const float* p2, int n, const double K[9],
-                                                double prob, double thr, int max_iters, double E[9], uint8_t* mask, int* found)
+static int emat_run(b200vo_ctx* ctx, const float* p1, const float* p2, int n, const double K[9], const int32_t* samples,
+                    double prob, double thr, int max_iters, double E[9], uint8_t* mask, int* found, int32_t* nmodels_out,
+                    int32_t* counts_out, double* models_out, int* winner_out, int* iters_run)
 {
     if (!ctx || !p1 || !p2 || !K || !E || !mask || !found) return B200VO_E_BADARG;
     *found = 0;
@@ -528,6 +530,7 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
     const double t = thr / ((a.fx + a.fy) / 2);
     a.thr_sq = (float)(t * t);
     a.conf = prob;
+    a.full = samples != nullptr;
     const int n_raw = 10 * iters + 256;
     const uint32_t* rng = nullptr;
     VO_TRY(vo_rng_table(ctx, n_raw, &rng));
@@ -547,7 +550,8 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
     uint8_t* d_small = d;                       // E[9] | result[3] | n | flags
     a.E = (double*)d_small; a.result = (int*)(d_small + 128); a.n_dev = (int*)(d_small + 192); a.flags = (int*)(d_small + 256);
     a.state = (int*)(d_small + 320);
-    VO_TRY(vo_reserve_pinned(ctx, 2 * b_p + b_mask + 1024));
+    const size_t b_dbg = samples ? b_s + b_nm + b_c + (models_out ? b_m : 0) : 0;
+    VO_TRY(vo_reserve_pinned(ctx, 2 * b_p + b_mask + 1024 + b_dbg));
     uint8_t* hp = (uint8_t*)ctx->h_pin;
     memcpy(hp, p1, (size_t)n * 8);
     memcpy(hp + b_p, p2, (size_t)n * 8);
@@ -559,7 +563,11 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
     VO_CUDA(ctx, cudaMemcpyAsync(a.n_dev, h_small, 4, cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA(ctx, cudaMemcpyAsync(a.state, h_small + 1, 16, cudaMemcpyHostToDevice, ctx->stream));
     emat_normalize_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a);
-    {
+    uint8_t* h_dbg = hp + 2 * b_p + b_mask + 1024;
+    if (samples) {   // the caller's sample set (parity runs: same hypotheses as the oracle / as cv2's RNG replay)
+        memcpy(h_dbg, samples, (size_t)iters * 5 * 4);
+        VO_CUDA(ctx, cudaMemcpyAsync(a.samples, h_dbg, (size_t)iters * 5 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
         const size_t smem = (size_t)n_raw * sizeof(int);
         if (smem > 48 * 1024)
             VO_CUDA(ctx, cudaFuncSetAttribute(ransac_samples_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -585,6 +593,11 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
     VO_CUDA(ctx, cudaGetLastError());
     VO_CUDA(ctx, cudaMemcpyAsync(hp, a.mask, b_mask, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(ctx, cudaMemcpyAsync(hp + b_mask, d_small, 512, cudaMemcpyDeviceToHost, ctx->stream));
+    if (samples) {
+        if (nmodels_out) VO_CUDA(ctx, cudaMemcpyAsync(h_dbg + b_s, a.nmodels, (size_t)iters * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (counts_out) VO_CUDA(ctx, cudaMemcpyAsync(h_dbg + b_s + b_nm, a.counts, (size_t)iters * EM_MAXM * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (models_out) VO_CUDA(ctx, cudaMemcpyAsync(h_dbg + b_s + b_nm + b_c, a.models, (size_t)iters * EM_MAXM * 72, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
@@ -596,5 +609,31 @@ extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1
         memcpy(E, hp + b_mask, 72);
         memcpy(mask, hp, (size_t)n);
     }
+    if (winner_out) *winner_out = res[2];
+    if (iters_run) *iters_run = res[1];
+    if (samples) {
+        if (nmodels_out) memcpy(nmodels_out, h_dbg + b_s, (size_t)iters * 4);
+        if (counts_out) memcpy(counts_out, h_dbg + b_s + b_nm, (size_t)iters * EM_MAXM * 4);
+        if (models_out) memcpy(models_out, h_dbg + b_s + b_nm + b_c, (size_t)iters * EM_MAXM * 72);
+    }
     return 0;
+}
+
+extern "C" int b200vo_find_essential_mat_ransac(b200vo_ctx* ctx, const float* p1, const float* p2, int n, const double K[9],
+                                                double prob, double thr, int max_iters, double E[9], uint8_t* mask, int* found)
+{
+    return emat_run(ctx, p1, p2, n, K, nullptr, prob, thr, max_iters, E, mask, found, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// Same RANSAC on the CALLER's 5-subsets (north_star: "inlier masks bit-exact given the same hypothesis sample set"):
+// every sample is solved and scored (no early exit), the replay of cv2's loop picks the winner; per-sample model
+// counts, per-(sample, model) inlier counts and the models themselves come back for comparison with the oracle.
+extern "C" int b200vo_find_essential_mat_ransac_samples(b200vo_ctx* ctx, const float* p1, const float* p2, int n, const double K[9],
+                                                        const int32_t* samples, int iters, double prob, double thr, double E[9],
+                                                        uint8_t* mask, int* found, int32_t* nmodels_out, int32_t* counts_out,
+                                                        double* models_out, int* winner_out, int* iters_run)
+{
+    if (!samples || iters < 1) return B200VO_E_BADARG;
+    return emat_run(ctx, p1, p2, n, K, samples, prob, thr, iters, E, mask, found, nmodels_out, counts_out, models_out, winner_out,
+                    iters_run);
 }

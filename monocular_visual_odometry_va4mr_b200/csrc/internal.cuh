@@ -62,6 +62,8 @@ struct b200vo_ctx {
     size_t h_pin_cap = 0;
     DevBuf d_scratch[8];     // generic device scratch (per-API use)
     FrameSlot slots[B200VO_MAX_SLOTS + 2];  // +2 internal slots for the stateless cv2-style call
+    DevBuf d_klt_queue;      // ring of work-queue counters for the persistent tracker kernel
+    unsigned klt_queue_next = 0;
     DevBuf d_rng;            // raw cv::RNG stream (uint32)
     int n_rng = 0;
     // tensor-map encode entry point (driver API, fetched lazily)

@@ -37,6 +37,7 @@ struct KltArgs {
     float eps_lo, eps_hi;   // eps_sq * (1 -+ 1e-6) in float: outside this band the float test decides
     // shared-memory carve-up (bytes, per warp)
     int patch_stride, smem_patch, smem_der, smem_iwin, smem_di, smem_per_warp;
+    int* queue;             // v3: [0] next feature slot, [1] warps that have found the queue empty (both 0 between launches)
 };
 
 __device__ __forceinline__ long long warp_sum_i64(int v)
@@ -257,6 +258,10 @@ klt_kernel(const KltArgs a)
 }
 
 #include "klt_v2.cuh"
+#include "klt_v3.cuh"
+
+#define KLT_QUEUE_SLOTS 1024
+#define KLT_QUEUE_INTS 8   // one 32-byte sector per slot
 
 int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,
                    const uint8_t* d_next_slab, size_t next_stride, int batch, const KltPointSet* sets, int n_sets,
@@ -294,14 +299,43 @@ int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab
     const long long total_warps = (long long)batch * (a.cap[0] + a.cap[1]);
     const unsigned grid = (unsigned)((total_warps + KLT_WARPS - 1) / KLT_WARPS);
     void (*kern)(const KltArgs) = nullptr;
-    if (kp.win_w == 21 && kp.win_h == 21) { kern = klt_kernel_v2<21, 21>; smem = (size_t)KV2<21, 21>::PER_WARP * KLT_WARPS + 64; }
+    // v3 = persistent warps + work queue (default); B200VO_KLT=v2 keeps the one-warp-per-slot kernel for A/B runs
+    static const bool use_v2 = getenv("B200VO_KLT") && !strcmp(getenv("B200VO_KLT"), "v2");
+    const bool sized = (kp.win_w == 21 && kp.win_h == 21) || (kp.win_w == 15 && kp.win_h == 15);
+    const bool v3 = sized && !use_v2 && total_warps < (1ll << 30);
+    unsigned launch_grid = grid;
+    int min_ctas = 0;
+    if (v3) {
+        if (kp.win_w == 21) { kern = klt_kernel_v3<21, 21>; smem = (size_t)KV3<21, 21>::PER_WARP * KLT_WARPS + 64; min_ctas = KV3<21, 21>::MIN_CTAS; }
+        else { kern = klt_kernel_v3<15, 15>; smem = (size_t)KV3<15, 15>::PER_WARP * KLT_WARPS + 64; min_ctas = KV3<15, 15>::MIN_CTAS; }
+        if (!ctx->d_klt_queue.p) {
+            VO_TRY(vo_reserve(ctx, ctx->d_klt_queue, (size_t)KLT_QUEUE_SLOTS * KLT_QUEUE_INTS * sizeof(int)));
+            VO_CUDA(ctx, cudaMemsetAsync(ctx->d_klt_queue.p, 0, (size_t)KLT_QUEUE_SLOTS * KLT_QUEUE_INTS * sizeof(int), ctx->stream));
+            VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // other streams of this context launch trackers too
+        }
+        // a ring of counters: launches that run concurrently (landmark / candidate sets, chunk streams) never share one,
+        // and each kernel re-arms its own slot when its last warp retires
+        a.queue = (int*)ctx->d_klt_queue.p + (size_t)(ctx->klt_queue_next++ % KLT_QUEUE_SLOTS) * KLT_QUEUE_INTS;
+        const unsigned resident = (unsigned)(ctx->num_sms * min_ctas);
+        launch_grid = grid < resident ? grid : resident;
+    }
+    else if (kp.win_w == 21 && kp.win_h == 21) { kern = klt_kernel_v2<21, 21>; smem = (size_t)KV2<21, 21>::PER_WARP * KLT_WARPS + 64; }
     else if (kp.win_w == 15 && kp.win_h == 15) { kern = klt_kernel_v2<15, 15>; smem = (size_t)KV2<15, 15>::PER_WARP * KLT_WARPS + 64; }
     else kern = klt_kernel<0, 0>;
-    if (smem > 48 * 1024)
-        VO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (kern != klt_kernel<0, 0>)   // the staged kernels live in shared memory: let 4 CTAs (64 registers each) fit
-        VO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    kern<<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(a);
+    {   // function attributes: once per kernel and process (the calls cost microseconds each on the launch path)
+        static void* configured[8] = {};
+        bool seen = false;
+        int free_slot = -1;
+        for (int i = 0; i < 8; ++i) { seen = seen || configured[i] == (void*)kern; if (!configured[i] && free_slot < 0) free_slot = i; }
+        if (!seen) {
+            if (smem > 48 * 1024)
+                VO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (kern != klt_kernel<0, 0>)   // the staged kernels live in shared memory: let 8 CTAs (64 registers each) fit
+                VO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            if (free_slot >= 0 && kern != klt_kernel<0, 0>) configured[free_slot] = (void*)kern;   // the generic kernel's smem size varies per call
+        }
+    }
+    kern<<<launch_grid, KLT_WARPS * 32, smem, ctx->stream>>>(a);
     ctx->launches++;
     VO_CUDA(ctx, cudaGetLastError());
     return 0;

@@ -205,19 +205,20 @@ __device__ inline void qr_lstsq6(const double* Ain, const double* bin, double* x
 #pragma unroll
         for (int i = k; i < M; ++i) vn += v[i] * v[i];
         if (vn == 0) continue;
+        const double tau = 2.0 / vn;      // H = I - tau v v^T: one division per reflector instead of one per column
 #pragma unroll
         for (int j = k; j < NC; ++j) {
             double s = 0;
 #pragma unroll
             for (int i = k; i < M; ++i) s += v[i] * A[i * NC + j];
-            s = 2 * s / vn;
+            s *= tau;
 #pragma unroll
             for (int i = k; i < M; ++i) A[i * NC + j] -= s * v[i];
         }
         double s = 0;
 #pragma unroll
         for (int i = k; i < M; ++i) s += v[i] * b[i];
-        s = 2 * s / vn;
+        s *= tau;
 #pragma unroll
         for (int i = k; i < M; ++i) b[i] -= s * v[i];
     }

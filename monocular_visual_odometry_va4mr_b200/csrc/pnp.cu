@@ -21,21 +21,10 @@ using namespace vo;
 // ------------------------------------------------------------------------------------------
 // 2. minimal solver: one thread per hypothesis
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
-pnp_solve_kernel(PnpArgs a)
+// One hypothesis: P3P on the first 3 points of the sample, the 4th picks the candidate.  Writes R|t (re-expanded
+// from rvec, as PnPRansacCallback stores its model) to h[12] and rvec to hr[3]; returns 0 when there is no model.
+__device__ inline int pnp_solve_one(const PnpArgs& a, const float* obj, const float* img, const int* smp, double* h, double* hr)
 {
-    const int b = blockIdx.y;
-    const int it = a.h_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= a.h_end) return;
-    if (!a.head && it >= a.need[b]) return;      // the sequential loop can no longer reach this hypothesis
-    const size_t hidx = (size_t)b * a.iters + it;
-    a.counts[hidx] = 0;
-    a.hyp_ok[hidx] = 0;
-    const int* smp = a.samples + hidx * 4;
-    const int N = a.n[b];
-    if (smp[0] < 0 || N < 4) return;
-    const float* obj = a.obj + (size_t)b * a.cap * 3;
-    const float* img = a.img + (size_t)b * a.cap * 2;
     double X[12], xn[8], uv[8];
     const double ifx = 1. / a.fx, ify = 1. / a.fy;
     for (int k = 0; k < 4; ++k) {
@@ -61,17 +50,32 @@ pnp_solve_kernel(PnpArgs a)
         if (!isfinite(e)) continue;
         if (best < 0 || e < best_e) { best = s; best_e = e; }
     }
-    if (best < 0) return;
+    if (best < 0) return 0;
     // the model is stored as rvec|tvec and re-expanded for scoring (as PnPRansacCallback does)
     double rv[3], Rr[9];
     R_to_rodrigues(R[best], rv);
     rodrigues_to_R(rv, Rr);
-    double* h = a.hyp + hidx * 12;
     for (int k = 0; k < 9; ++k) h[k] = Rr[k];
     for (int k = 0; k < 3; ++k) h[9 + k] = t[best][k];
-    double* hr = a.hyp_rvec + hidx * 3;
     hr[0] = rv[0]; hr[1] = rv[1]; hr[2] = rv[2];
-    a.hyp_ok[hidx] = 1;
+    return 1;
+}
+
+__global__ void __launch_bounds__(64)
+pnp_solve_kernel(PnpArgs a)
+{
+    const int b = blockIdx.y;
+    const int it = a.h_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= a.h_end) return;
+    if (!a.head && it >= a.need[b]) return;      // the sequential loop can no longer reach this hypothesis
+    const size_t hidx = (size_t)b * a.iters + it;
+    a.counts[hidx] = 0;
+    a.hyp_ok[hidx] = 0;
+    const int* smp = a.samples + hidx * 4;
+    const int N = a.n[b];
+    if (smp[0] < 0 || N < 4) return;
+    a.hyp_ok[hidx] = pnp_solve_one(a, a.obj + (size_t)b * a.cap * 3, a.img + (size_t)b * a.cap * 2, smp, a.hyp + hidx * 12,
+                                   a.hyp_rvec + hidx * 3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -243,90 +247,123 @@ pnp_select_kernel(PnpArgs a)
 // 5. EPnP refit on the inliers (OpenCV epnp.cpp algorithm, float64 inputs)
 // ------------------------------------------------------------------------------------------
 #define EPNP_T 256
+#define EPNP_JT 160   // threads of the block that take part in the 12x12 eigen-decomposition (144 elements, 5 warps)
 
-// Symmetric 12x12 eigen-decomposition by two-sided Jacobi rotations, executed by ONE WARP with the
-// round-robin (tournament) ordering: 11 rounds per sweep, 6 disjoint (p,q) pairs per round, all six
-// rotations of a round applied together (columns, then rows, then the eigenvector columns).
-// A (in/out, destroyed) and V (out, eigenvectors in columns) live in shared memory, row-major 12x12.
-// Only used for EPnP's M^T M, where the result is independent of eigenvector signs and of the
-// rotation order (unlike the 3x3 control-point SVD, which replays OpenCV's order exactly).
-__device__ inline void warp_jacobi_eig12(double* A, double* V, double* cs /* [12] + pair table */, int lane)
+__device__ __forceinline__ void bar_jacobi() { asm volatile("bar.sync 1, %0;" ::"n"(EPNP_JT) : "memory"); }
+
+// 1/x to ~1 ulp without the IEEE division routine: hardware seed (2^-23) + two Newton steps
+__device__ __forceinline__ double fast_rcp(double x)
 {
-    // pair table of the tournament: pq[rnd][pr] = p | q << 8 (p < q), built once
-    unsigned short* pq = reinterpret_cast<unsigned short*>(cs + 12);
-    for (int k = lane; k < 66; k += 32) {
-        const int rnd = k / 6, pr = k - rnd * 6;
-        int p = pr == 0 ? 11 : (rnd + pr) % 11;
-        int q = (rnd + 11 - pr) % 11;
-        if (p > q) { const int t = p; p = q; q = t; }
-        pq[k] = (unsigned short)(p | (q << 8));
-    }
-    for (int k = lane; k < 144; k += 32) V[k] = (k / 12 == k % 12) ? 1.0 : 0.0;
-    // this lane's fixed element slots: columns pass (A and V: 12 rows x 6 pairs x 2 matrices = 144), rows pass (12 x 6 = 72)
-    int c_row[5], c_pr[5], r_k[3], r_pr[3];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const int e = lane + 32 * i, m = e / 72, r = (e % 72) / 6;
-        c_pr[i] = e % 6;
-        c_row[i] = e < 144 ? m * 144 + r * 12 : -1;       // V follows A in shared memory (A + 144)
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int e = lane + 32 * i;
-        r_pr[i] = e % 6;
-        r_k[i] = e < 72 ? e / 6 : -1;
-    }
-    __syncwarp();
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+struct EpnpShared {
+    double red[8 * 56];
+    double out[56];
+    double cws[4][3];
+    double ci[9];       // inverse of the control-point basis
+    double v4[4][12];   // eigenvectors of MtM for the 4 smallest eigenvalues, smallest first
+    double L[60], rho[6];
+    double Rs[3][9], ts[3][3];
+    double mom_aX[12];  // sum_i alpha_ij X_ik
+    double mom_a[4];    // sum_i alpha_ij
+    double alpha0[4];   // barycentric coords of the first inlier (solve_for_sign)
+    double jac[2][288]; // double-buffered [A (12x12) | V (12x12)]
+    double rc[EPNP_JT / 32][12], rs[EPNP_JT / 32][12];   // per warp: this round's rotation seen from index k: x_k' = rc[k] x_k + rs[k] x_partner(k)
+    unsigned char partner[11 * 12];
+};
+
+// 1/sqrt(x) for x in the float32 range: hardware float seed (22 bits) + two Newton steps in double (full precision).
+// Far cheaper than the library rsqrt() on a part whose FP64 pipe has a long dependent-issue latency.
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    float xf = (float)x, yf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(xf));
+    double y = (double)yf;
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return y;
+}
+
+// Symmetric 12x12 eigen-decomposition by two-sided Jacobi rotations with the round-robin (tournament) ordering:
+// 11 rounds per sweep, 6 disjoint (p,q) pairs per round.  One thread per matrix element: A' = J^T A J and V' = V J
+// are each ONE read-compute-write pass per round (the old form needed a column pass, a row pass and three warp
+// barriers on one warp), double-buffered so that a round costs ONE block barrier: every warp computes the round's six
+// rotations for itself (lanes 0-5, a warp-private copy in shared memory, __syncwarp) instead of waiting for one warp
+// to publish them.  The rotation is the small-angle solution in half-angle form,
+//     c = sqrt((1 + |d|/h) / 2),  s = sgn(d) b / (2 h c),   d = a_qq - a_pp, b = 2 a_pq, h = sqrt(d^2 + b^2),
+// i.e. two reciprocal square roots and no division (1 + |d|/h never cancels).
+// Called by threads [0, EPNP_JT); S.jac[0][0..143] holds A on entry.  Returns the buffer index holding the result
+// (A's diagonal = eigenvalues, V's columns = eigenvectors).  Only used for EPnP's M^T M, where the result is
+// independent of eigenvector signs and of the rotation order (unlike the 3x3 control-point SVD, which replays
+// OpenCV's order exactly).
+__device__ inline int block_jacobi_eig12(EpnpShared& S, int tid)
+{
+    const bool act = tid < 144;
+    const int i = act ? tid / 12 : 0, j = act ? tid - 12 * i : 0;
+    const int lane = tid & 31, warp = tid >> 5;
+    double* rc = S.rc[warp];
+    double* rs = S.rs[warp];
+    if (act) S.jac[0][144 + tid] = (i == j) ? 1.0 : 0.0;
+    int cur = 0;
+    bar_jacobi();
     for (int sweep = 0; sweep < 30; ++sweep) {
-        // convergence: sum of squared off-diagonal entries relative to the diagonal
-        double off = 0, dia = 0;
-        for (int k = lane; k < 144; k += 32) {
-            const double v = A[k];
-            if (k / 12 == k % 12) dia += v * v; else off += v * v;
-        }
+        {   // convergence: squared off-diagonal mass relative to the diagonal (every warp for itself: no barrier)
+            const double* A = S.jac[cur];
+            double off = 0, dia = 0;
+            for (int k = lane; k < 144; k += 32) {
+                const double v = A[k];
+                if (k / 12 == k % 12) dia += v * v; else off += v * v;
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dia += __shfl_xor_sync(0xffffffffu, dia, o); }
-        if (off <= 1e-30 * dia || off == 0) break;
+            for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dia += __shfl_xor_sync(0xffffffffu, dia, o); }
+            if (off <= 1e-30 * dia || off == 0) return cur;     // same value in every warp: uniform exit
+        }
         for (int rnd = 0; rnd < 11; ++rnd) {
+            const double* A = S.jac[cur];
             if (lane < 6) {
-                const int pqv = pq[rnd * 6 + lane], p = pqv & 0xff, q = pqv >> 8;
+                int p = lane == 0 ? 11 : (rnd + lane) % 11;
+                int q = (rnd + 11 - lane) % 11;
+                if (p > q) { const int t = p; p = q; q = t; }
                 const double apq = A[p * 12 + q];
                 double c = 1.0, sn = 0.0;
-                if (fabs(apq) > 1e-300) {
-                    const double theta = (A[q * 12 + q] - A[p * 12 + p]) / (2 * apq);
+                const double d = A[q * 12 + q] - A[p * 12 + p], b2 = 2 * apq;
+                const double hh = d * d + b2 * b2;
+                if (fabs(apq) > 1e-300 && hh > 1e-30 && hh < 1e30) {
+                    const double rh = fast_rsqrt(hh);
+                    const double u = fma(0.5 * fabs(d), rh, 0.5);        // (1 + |d|/h) / 2 in [0.5, 1]
+                    const double ru = fast_rsqrt(u);
+                    c = u * ru;
+                    sn = (d >= 0 ? 0.5 : -0.5) * b2 * rh * ru;
+                } else if (fabs(apq) > 1e-300) {                         // outside the float range of the seed: the slow exact form
+                    const double theta = d / b2;
                     const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
                     c = 1 / sqrt(t * t + 1); sn = t * c;
                 }
-                cs[2 * lane] = c; cs[2 * lane + 1] = sn;
+                if (!isfinite(c) || !isfinite(sn)) { c = 1.0; sn = 0.0; }
+                rc[p] = c; rs[p] = -sn;     // x_p' = c x_p - s x_q
+                rc[q] = c; rs[q] = sn;      // x_q' = s x_p + c x_q
             }
             __syncwarp();
-            // columns p,q of A and of V
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                if (c_row[i] >= 0) {
-                    const int pqv = pq[rnd * 6 + c_pr[i]], p = pqv & 0xff, q = pqv >> 8;
-                    const double c = cs[2 * c_pr[i]], sn = cs[2 * c_pr[i] + 1];
-                    double* M = A + c_row[i];
-                    const double x = M[p], y = M[q];
-                    M[p] = c * x - sn * y;
-                    M[q] = sn * x + c * y;
-                }
+            if (act) {
+                const int pi = S.partner[rnd * 12 + i], pj = S.partner[rnd * 12 + j];
+                const double ci_ = rc[i], si_ = rs[i], cj = rc[j], sj = rs[j];
+                const double b_ij = cj * A[i * 12 + j] + sj * A[i * 12 + pj];        // (A J)[i][j]
+                const double b_pj = cj * A[pi * 12 + j] + sj * A[pi * 12 + pj];      // (A J)[partner(i)][j]
+                double* Nx = S.jac[cur ^ 1];
+                Nx[i * 12 + j] = ci_ * b_ij + si_ * b_pj;                             // (J^T A J)[i][j]
+                Nx[144 + i * 12 + j] = cj * A[144 + i * 12 + j] + sj * A[144 + i * 12 + pj];
             }
-            __syncwarp();
-            // rows p,q of A
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                if (r_k[i] >= 0) {
-                    const int pqv = pq[rnd * 6 + r_pr[i]], p = pqv & 0xff, q = pqv >> 8;
-                    const double c = cs[2 * r_pr[i]], sn = cs[2 * r_pr[i] + 1];
-                    const double x = A[p * 12 + r_k[i]], y = A[q * 12 + r_k[i]];
-                    A[p * 12 + r_k[i]] = c * x - sn * y;
-                    A[q * 12 + r_k[i]] = sn * x + c * y;
-                }
-            }
-            __syncwarp();
+            bar_jacobi();
+            cur ^= 1;
         }
     }
+    return cur;
 }
 
 template <int NV>
@@ -349,29 +386,13 @@ __device__ __forceinline__ void block_reduce_sum(double* v, double* s_red /* [8]
     __syncthreads();
 }
 
-struct EpnpShared {
-    double red[8 * 40];
-    double out[40];
-    double cws[4][3];
-    double ci[9];       // inverse of the control-point basis
-    double ut[144];     // rows: singular vectors of MtM, descending singular value
-    double L[60], rho[6];
-    double Rs[3][9], ts[3][3];
-    double errs[3];
-    double mom_aX[12];  // sum_i alpha_ij X_ik
-    double mom_a[4];    // sum_i alpha_ij
-    double alpha0[4];   // barycentric coords of the first inlier (solve_for_sign)
-    double work[3 * 144 + 12];
-};
-
 __device__ inline void epnp_pose_from_betas(EpnpShared& S, const double* betas, double n, const double* Xbar, double* R, double* t)
 {
-    const double* v[4] = {S.ut + 12 * 11, S.ut + 12 * 10, S.ut + 12 * 9, S.ut + 12 * 8};
     double ccs[4][3];
     for (int i = 0; i < 4; ++i)
         for (int k = 0; k < 3; ++k) {
             double s = 0;
-            for (int j = 0; j < 4; ++j) s += betas[j] * v[j][3 * i + k];
+            for (int j = 0; j < 4; ++j) s += betas[j] * S.v4[j][3 * i + k];
             ccs[i][k] = s;
         }
     // solve_for_sign: z of the first point in the camera frame
@@ -420,26 +441,25 @@ __device__ inline void epnp_gauss_newton(const double* L, const double* rho, dou
     }
 }
 
-__global__ void __launch_bounds__(EPNP_T)
-pnp_epnp_kernel(PnpArgs a)
+// The refit, executed by one CTA of EPNP_T threads (every thread must call it; S is the CTA's scratch):
+// obj/img are this sequence's correspondences, inl[0..M) the inlier indices, pose_out receives rvec|tvec
+// (left untouched when the result is not finite -- the caller has put the RANSAC model there).
+__device__ inline void epnp_block(const PnpArgs& a, EpnpShared& S, const float* obj, const float* img, const int* inl, int M, double* pose_out)
 {
-    extern __shared__ __align__(16) uint8_t epnp_smem[];
-    EpnpShared& S = *reinterpret_cast<EpnpShared*>(epnp_smem);
-    const int b = blockIdx.x;
-    if (!a.ok[b]) return;
-    const int N = a.n[b];
-    const int M = a.n_inliers[b];
-    if (N == 4 || M < 4) return;   // N == 4: cv2 returns the direct P3P solve
-    const float* obj = a.obj + (size_t)b * a.cap * 3;
-    const float* img = a.img + (size_t)b * a.cap * 2;
-    const int* inl = a.inliers + (size_t)b * a.cap;
+    const int tid = threadIdx.x;
     const double n = (double)M;
     const double ifx = 1. / a.fx, ify = 1. / a.fy;
-
+    // tournament partner table (built here, consumed after several barriers)
+    for (int k = tid; k < 66; k += EPNP_T) {
+        const int rnd = k / 6, pr = k - rnd * 6;
+        const int p = pr == 0 ? 11 : (rnd + pr) % 11, q = (rnd + 11 - pr) % 11;
+        S.partner[rnd * 12 + p] = (unsigned char)q;
+        S.partner[rnd * 12 + q] = (unsigned char)p;
+    }
     // pass 1: centroid
-    double acc[40];
+    double acc[28];
     acc[0] = acc[1] = acc[2] = 0;
-    for (int k = threadIdx.x; k < M; k += EPNP_T) {
+    for (int k = tid; k < M; k += EPNP_T) {
         const float* o = obj + 3 * inl[k];
         acc[0] += (double)o[0]; acc[1] += (double)o[1]; acc[2] += (double)o[2];
     }
@@ -448,13 +468,13 @@ pnp_epnp_kernel(PnpArgs a)
     __syncthreads();
     // pass 2: PW0^T PW0
     for (int k = 0; k < 6; ++k) acc[k] = 0;
-    for (int k = threadIdx.x; k < M; k += EPNP_T) {
+    for (int k = tid; k < M; k += EPNP_T) {
         const float* o = obj + 3 * inl[k];
         const double x = (double)o[0] - c0[0], y = (double)o[1] - c0[1], z = (double)o[2] - c0[2];
         acc[0] += x * x; acc[1] += x * y; acc[2] += x * z; acc[3] += y * y; acc[4] += y * z; acc[5] += z * z;
     }
     block_reduce_sum<6>(acc, S.red, S.out);
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         const double Sm[9] = {S.out[0], S.out[1], S.out[2], S.out[1], S.out[3], S.out[4], S.out[2], S.out[4], S.out[5]};
         double W[3], U[9], Vt[9], At[9];
         jacobi_svd<3>(Sm, W, U, Vt, At);
@@ -468,13 +488,15 @@ pnp_epnp_kernel(PnpArgs a)
         if (!inv3(cc, S.ci)) for (int k = 0; k < 9; ++k) S.ci[k] = nan("");
     }
     __syncthreads();
-    // pass 3: barycentric coordinates; M^T M in its 4x4-blocks-of-3x3 structure (40 sums) and moments
+    // pass 3: barycentric coordinates; M^T M in its 4x4-blocks-of-3x3 structure (40 sums) and the moments (16 sums).
+    // The 56 sums are split over the two halves of the CTA (28 accumulators per thread instead of 56: the kernel has
+    // to fit two CTAs per SM beside the tracker): threads 0-127 take the block pairs (0,0) (0,1) (0,2) (0,3) (1,1) and
+    // the moments of alpha_0, alpha_1; threads 128-255 the pairs (1,2) (1,3) (2,2) (2,3) (3,3) and alpha_2, alpha_3.
     double ci[9];
     for (int k = 0; k < 9; ++k) ci[k] = S.ci[k];
-    for (int k = 0; k < 40; ++k) acc[k] = 0;
-    double mo[16];
-    for (int k = 0; k < 16; ++k) mo[k] = 0;
-    for (int k = threadIdx.x; k < M; k += EPNP_T) {
+    for (int k = 0; k < 28; ++k) acc[k] = 0;
+    const int grp = tid >> 7;
+    for (int k = tid & 127; k < M; k += EPNP_T / 2) {
         const int id = inl[k];
         const float* o = obj + 3 * id;
         const double X = o[0], Y = o[1], Z = o[2];
@@ -486,80 +508,97 @@ pnp_epnp_kernel(PnpArgs a)
         const double u = (((double)img[2 * id] - a.cx) * ifx) * a.fx + a.cx;
         const double v = (((double)img[2 * id + 1] - a.cy) * ify) * a.fy + a.cy;
         const double du = a.cx - u, dv = a.cy - v, dd = du * du + dv * dv;
-        int q = 0;
-        for (int j = 0; j < 4; ++j)
-            for (int l = j; l < 4; ++l, ++q) {
-                const double aa = al[j] * al[l];
-                acc[4 * q] += aa; acc[4 * q + 1] += aa * du; acc[4 * q + 2] += aa * dv; acc[4 * q + 3] += aa * dd;
-            }
-        for (int j = 0; j < 4; ++j) {
-            mo[3 * j] += al[j] * X; mo[3 * j + 1] += al[j] * Y; mo[3 * j + 2] += al[j] * Z;
-            mo[12 + j] += al[j];
+#define EPNP_PAIR(slot, j, l) { const double aa = al[j] * al[l]; acc[4 * (slot)] += aa; acc[4 * (slot) + 1] += aa * du; \
+                                acc[4 * (slot) + 2] += aa * dv; acc[4 * (slot) + 3] += aa * dd; }
+#define EPNP_MOM(slot, j) { acc[20 + 3 * (slot)] += al[j] * X; acc[20 + 3 * (slot) + 1] += al[j] * Y; acc[20 + 3 * (slot) + 2] += al[j] * Z; \
+                            acc[26 + (slot)] += al[j]; }
+        if (grp == 0) {
+            EPNP_PAIR(0, 0, 0) EPNP_PAIR(1, 0, 1) EPNP_PAIR(2, 0, 2) EPNP_PAIR(3, 0, 3) EPNP_PAIR(4, 1, 1)
+            EPNP_MOM(0, 0) EPNP_MOM(1, 1)
+            if (k == 0) for (int j = 0; j < 4; ++j) S.alpha0[j] = al[j];
+        } else {
+            EPNP_PAIR(0, 1, 2) EPNP_PAIR(1, 1, 3) EPNP_PAIR(2, 2, 2) EPNP_PAIR(3, 2, 3) EPNP_PAIR(4, 3, 3)
+            EPNP_MOM(0, 2) EPNP_MOM(1, 3)
         }
-        if (k == 0) for (int j = 0; j < 4; ++j) S.alpha0[j] = al[j];
+#undef EPNP_PAIR
+#undef EPNP_MOM
     }
-    block_reduce_sum<40>(acc, S.red, S.out);
-    double Xbar[3];
-    if (threadIdx.x == 0) {
-        // assemble the 12x12 M^T M
-        double* MtM = S.work;
-        int q = 0;
-        for (int j = 0; j < 4; ++j)
-            for (int l = j; l < 4; ++l, ++q) {
-                const double A = S.out[4 * q], B = S.out[4 * q + 1], Cc = S.out[4 * q + 2], D = S.out[4 * q + 3];
-                const double blk[9] = {a.fx * a.fx * A, 0, a.fx * B, 0, a.fy * a.fy * A, a.fy * Cc, a.fx * B, a.fy * Cc, D};
-                for (int r = 0; r < 3; ++r)
-                    for (int c = 0; c < 3; ++c) {
-                        MtM[(3 * j + r) * 12 + 3 * l + c] = blk[3 * r + c];
-                        MtM[(3 * l + c) * 12 + 3 * j + r] = blk[3 * r + c];
-                    }
+    {   // reduce: warps 0-3 hold the first 28 sums, warps 4-7 the other 28
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int k = 0; k < 28; ++k) {
+            double x = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) S.red[warp * 28 + k] = x;
+        }
+        __syncthreads();
+        if (tid < 56) {
+            const int g = tid / 28, kk = tid - 28 * g;
+            double x = 0;
+            for (int w = 0; w < 4; ++w) x += S.red[(4 * g + w) * 28 + kk];
+            // S.out: [0,40) the ten (j <= l) block sums x 4, [40,52) sum alpha_j X, [52,56) sum alpha_j
+            const int dst = kk < 20 ? 20 * g + kk : (kk < 26 ? 40 + 6 * g + (kk - 20) : 52 + 2 * g + (kk - 26));
+            S.out[dst] = x;
+        }
+        __syncthreads();
+    }
+    if (tid < 144) {
+        // assemble the 12x12 M^T M, one element per thread: block (jb, lb) of the 4x4 block structure, entry (r, c)
+        const int row = tid / 12, col = tid - 12 * row;
+        int jb = row / 3, r = row - 3 * jb, lb = col / 3, c = col - 3 * lb;
+        if (jb > lb) { int t = jb; jb = lb; lb = t; t = r; r = c; c = t; }      // symmetric: blk(l,j) = blk(j,l)^T
+        const int q = jb * 4 - jb * (jb - 1) / 2 + (lb - jb);                    // index of (jb <= lb) in the upper triangle
+        const double A = S.out[4 * q], B = S.out[4 * q + 1], Cc = S.out[4 * q + 2], D = S.out[4 * q + 3];
+        double v;
+        if (r == 0 && c == 0) v = a.fx * a.fx * A;
+        else if (r == 1 && c == 1) v = a.fy * a.fy * A;
+        else if (r == 2 && c == 2) v = D;
+        else if ((r == 0 && c == 2) || (r == 2 && c == 0)) v = a.fx * B;
+        else if ((r == 1 && c == 2) || (r == 2 && c == 1)) v = a.fy * Cc;
+        else v = 0.0;
+        S.jac[0][tid] = v;
+    }
+    if (tid >= 160 && tid < 172) S.mom_aX[tid - 160] = S.out[40 + tid - 160];
+    if (tid >= 172 && tid < 176) S.mom_a[tid - 172] = S.out[52 + tid - 172];
+    __syncthreads();
+    const double Xbar[3] = {c0[0], c0[1], c0[2]};
+    if (tid < EPNP_JT) {
+        const int cur = block_jacobi_eig12(S, tid);
+        const double* A = S.jac[cur];
+        if (tid < 12) {
+            // rank of eigenvalue tid in DESCENDING order (stable); cvSVD(MtM, D, Ut) rows 11, 10, 9, 8 = the four smallest
+            const double lam = A[tid * 13];
+            int rank = 0;
+            for (int m = 0; m < 12; ++m) {
+                const double lm = A[m * 13];
+                rank += (lm > lam || (lm == lam && m < tid)) ? 1 : 0;
             }
-    }
-    __syncthreads();
-    block_reduce_sum<16>(mo, S.red, S.out);
-    if (threadIdx.x < 12) S.mom_aX[threadIdx.x] = S.out[threadIdx.x];
-    if (threadIdx.x < 4) S.mom_a[threadIdx.x] = S.out[12 + threadIdx.x];
-    __syncthreads();
-    Xbar[0] = c0[0]; Xbar[1] = c0[1]; Xbar[2] = c0[2];
-    if (threadIdx.x < 32) {
-        double* MtM = S.work;          // destroyed: its diagonal becomes the eigenvalues
-        double* Vm = S.work + 144;     // eigenvectors in columns
-        warp_jacobi_eig12(MtM, Vm, S.work + 288, threadIdx.x);
-        __syncwarp();
-        if (threadIdx.x == 0) {
-            // rows of ut = eigenvectors by DESCENDING eigenvalue (what cvSVD(MtM, D, Ut) returns)
-            int order[12];
-            for (int i = 0; i < 12; ++i) order[i] = i;
-            for (int i = 0; i < 12; ++i)
-                for (int j = i + 1; j < 12; ++j)
-                    if (MtM[order[j] * 13] > MtM[order[i] * 13]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
-            for (int i = 0; i < 12; ++i)
-                for (int k = 0; k < 12; ++k) S.ut[12 * i + k] = Vm[12 * k + order[i]];
+            if (rank >= 8)
+                for (int k = 0; k < 12; ++k) S.v4[11 - rank][k] = A[144 + 12 * k + tid];
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const double* v[4] = {S.ut + 12 * 11, S.ut + 12 * 10, S.ut + 12 * 9, S.ut + 12 * 8};
+    if (tid < 6) {
         const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
-        double dv[4][6][3];
-        for (int i = 0; i < 4; ++i)
-            for (int j = 0; j < 6; ++j)
-                for (int k = 0; k < 3; ++k) dv[i][j][k] = v[i][3 * pa[j] + k] - v[i][3 * pb[j] + k];
+        const int i = tid;
+        double dv[4][3];
+        for (int m = 0; m < 4; ++m)
+            for (int k = 0; k < 3; ++k) dv[m][k] = S.v4[m][3 * pa[i] + k] - S.v4[m][3 * pb[i] + k];
 #define VDOT(p, q) ((p)[0] * (q)[0] + (p)[1] * (q)[1] + (p)[2] * (q)[2])
-        for (int i = 0; i < 6; ++i) {
-            double* r = S.L + 10 * i;
-            r[0] = VDOT(dv[0][i], dv[0][i]); r[1] = 2 * VDOT(dv[0][i], dv[1][i]); r[2] = VDOT(dv[1][i], dv[1][i]);
-            r[3] = 2 * VDOT(dv[0][i], dv[2][i]); r[4] = 2 * VDOT(dv[1][i], dv[2][i]); r[5] = VDOT(dv[2][i], dv[2][i]);
-            r[6] = 2 * VDOT(dv[0][i], dv[3][i]); r[7] = 2 * VDOT(dv[1][i], dv[3][i]); r[8] = 2 * VDOT(dv[2][i], dv[3][i]);
-            r[9] = VDOT(dv[3][i], dv[3][i]);
-            const double d[3] = {S.cws[pa[i]][0] - S.cws[pb[i]][0], S.cws[pa[i]][1] - S.cws[pb[i]][1], S.cws[pa[i]][2] - S.cws[pb[i]][2]};
-            S.rho[i] = VDOT(d, d);
-        }
+        double* r = S.L + 10 * i;
+        r[0] = VDOT(dv[0], dv[0]); r[1] = 2 * VDOT(dv[0], dv[1]); r[2] = VDOT(dv[1], dv[1]);
+        r[3] = 2 * VDOT(dv[0], dv[2]); r[4] = 2 * VDOT(dv[1], dv[2]); r[5] = VDOT(dv[2], dv[2]);
+        r[6] = 2 * VDOT(dv[0], dv[3]); r[7] = 2 * VDOT(dv[1], dv[3]); r[8] = 2 * VDOT(dv[2], dv[3]);
+        r[9] = VDOT(dv[3], dv[3]);
+        const double d[3] = {S.cws[pa[i]][0] - S.cws[pb[i]][0], S.cws[pa[i]][1] - S.cws[pb[i]][1], S.cws[pa[i]][2] - S.cws[pb[i]][2]};
+        S.rho[i] = VDOT(d, d);
     }
     __syncthreads();
-    // three beta initialisations (one lane each), 5 Gauss-Newton steps, pose from the moments
-    if (threadIdx.x < 3) {
-        const int Nn = threadIdx.x + 1;
+    // three beta initialisations, one per WARP (their code paths differ: lanes of one warp would run them one
+    // after the other), 5 Gauss-Newton steps each, pose from the moments
+    if ((tid & 31) == 0 && tid < 96) {
+        const int Nn = (tid >> 5) + 1;
         const double* L = S.L;
         double be[4] = {0, 0, 0, 0};
         if (Nn == 1) {
@@ -585,12 +624,12 @@ pnp_epnp_kernel(PnpArgs a)
             be[2] = b5[3] / be[0];
         }
         epnp_gauss_newton(S.L, S.rho, be);
-        epnp_pose_from_betas(S, be, n, Xbar, S.Rs[threadIdx.x], S.ts[threadIdx.x]);
+        epnp_pose_from_betas(S, be, n, Xbar, S.Rs[Nn - 1], S.ts[Nn - 1]);
     }
     __syncthreads();
     // pass 4: mean reprojection error of the three candidates
     acc[0] = acc[1] = acc[2] = 0;
-    for (int k = threadIdx.x; k < M; k += EPNP_T) {
+    for (int k = tid; k < M; k += EPNP_T) {
         const int id = inl[k];
         const float* o = obj + 3 * id;
         const double X = o[0], Y = o[1], Z = o[2];
@@ -609,7 +648,7 @@ pnp_epnp_kernel(PnpArgs a)
         }
     }
     block_reduce_sum<3>(acc, S.red, S.out);
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         const double r1 = S.out[0] / n, r2 = S.out[1] / n, r3 = S.out[2] / n;
         int Nn = 0;
         double rb = r1;
@@ -619,12 +658,264 @@ pnp_epnp_kernel(PnpArgs a)
         for (int k = 0; k < 9; ++k) fin = fin && isfinite(S.Rs[Nn][k]);
         for (int k = 0; k < 3; ++k) fin = fin && isfinite(S.ts[Nn][k]);
         if (fin) {
-            double* pose = a.pose + (size_t)b * 6;
             double rv[3];
             R_to_rodrigues(S.Rs[Nn], rv);
-            pose[0] = rv[0]; pose[1] = rv[1]; pose[2] = rv[2];
-            pose[3] = S.ts[Nn][0]; pose[4] = S.ts[Nn][1]; pose[5] = S.ts[Nn][2];
+            pose_out[0] = rv[0]; pose_out[1] = rv[1]; pose_out[2] = rv[2];
+            pose_out[3] = S.ts[Nn][0]; pose_out[4] = S.ts[Nn][1]; pose_out[5] = S.ts[Nn][2];
         }
+    }
+}
+
+__global__ void __launch_bounds__(EPNP_T)
+pnp_epnp_kernel(PnpArgs a)
+{
+    extern __shared__ __align__(16) uint8_t epnp_smem[];
+    EpnpShared& S = *reinterpret_cast<EpnpShared*>(epnp_smem);
+    const int b = blockIdx.x;
+    if (!a.ok[b]) return;
+    const int N = a.n[b];
+    const int M = a.n_inliers[b];
+    if (N == 4 || M < 4) return;   // N == 4: cv2 returns the direct P3P solve
+    epnp_block(a, S, a.obj + (size_t)b * a.cap * 3, a.img + (size_t)b * a.cap * 2, a.inliers + (size_t)b * a.cap, M,
+               a.pose + (size_t)b * 6);
+}
+
+// ------------------------------------------------------------------------------------------
+// 6. the whole pose chain of one sequence in ONE CTA (the per-frame path: N <= a few thousand correspondences)
+// ------------------------------------------------------------------------------------------
+// status==1 compaction -> [ 32 cv::RNG subsets -> 32 P3P solves -> score them on every point -> replay cv2's loop ]
+// repeated while the adaptive stop still wants hypotheses (typically once: at 10 % outliers cv2 stops after ~5)
+// -> winner mask + ordered inlier list -> EPnP refit -> mask over the original landmark slots.
+// Same device functions as the multi-kernel path (pnp_solve_one, pnp_is_inlier, epnp_block), so the results are
+// the same bits; what disappears is nine dependent launches of one-CTA-per-sequence kernels and the global
+// round trips between them (250 us -> one launch), which is what bounds a single sequence and small shards.
+#define FUSED_T EPNP_T
+#define FUSED_CHUNK 32
+#define FUSED_WIN 256     // raw RNG values looked at per sampling pass
+
+struct PoseFusedShared {
+    double h[FUSED_CHUNK * 12];
+    double rv[FUSED_CHUNK * 3];
+    double win_h[12], win_rv[3];
+    int ok[FUSED_CHUNK], cnt[FUSED_CHUNK];
+    int smp[FUSED_CHUNK * 4];
+    int mod[FUSED_WIN];
+    int warp_n[8];
+    int base, N, niters, max_good, win, it0, pos, nh;
+};
+
+// cv::RNG subsets for hypotheses [it0, it0 + nh): one warp; `pos` = position in the raw stream (carried between chunks)
+__device__ inline void fused_draw_samples(const PnpArgs& a, PoseFusedShared& F, int b, int N, int nh, int lane)
+{
+    int i0 = 0;
+    int pos = F.pos;
+    while (i0 < nh) {
+        // residues of the next FUSED_WIN raw values
+        for (int k = lane; k < FUSED_WIN; k += 32) F.mod[k] = pos + k < a.n_raw ? (int)(a.rng_raw[pos + k] % (uint32_t)N) : -1;
+        __syncwarp();
+        const int i = i0 + lane, p = 4 * lane;
+        const bool live = i < nh;
+        int sv[4] = {0, 0, 0, 0};
+        bool bad = false;
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sv[j] = F.mod[p + j];
+            bad = sv[3] < 0 || sv[0] < 0 || sv[1] < 0 || sv[2] < 0;   // raw table exhausted
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+#pragma unroll
+                for (int m = 0; m < j; ++m) bad = bad || (sv[j] == sv[m]);
+        }
+        const unsigned stop = __ballot_sync(0xffffffffu, live && bad);
+        const int first = stop ? __ffs(stop) - 1 : 32;
+        if (live && lane < first) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) F.smp[4 * i + j] = sv[j];
+        }
+        if (first == 32) { pos += 4 * (nh - i0); i0 = nh; break; }
+        int npos = 0;
+        if (lane == first) {   // getSubset's redraw loop, sequentially, for this one sample (straight from the raw table)
+            int q = pos + p, idx[4] = {-1, -1, -1, -1};
+            bool okk = true;
+            for (int j = 0; j < 4 && okk; ++j) {
+                for (;;) {
+                    if (q >= a.n_raw) { okk = false; break; }
+                    const int v = (int)(a.rng_raw[q++] % (uint32_t)N);
+                    bool d = false;
+                    for (int m = 0; m < j; ++m) d = d || (idx[m] == v);
+                    if (!d) { idx[j] = v; break; }
+                }
+            }
+            if (!okk) {
+                idx[0] = idx[1] = idx[2] = idx[3] = -1;
+                a.flags[b] |= 1;
+                q = a.n_raw;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) F.smp[4 * i + j] = idx[j];
+            npos = q;
+        }
+        pos = __shfl_sync(0xffffffffu, npos, first);
+        i0 += first + 1;
+        __syncwarp();
+    }
+    if (lane == 0) F.pos = pos;
+}
+
+template <int MIN_CTAS>   // 1: every register the SM has (lowest latency); 2: two CTAs per SM, i.e. room for four tracker CTAs beside one
+__global__ void __launch_bounds__(FUSED_T, MIN_CTAS)
+pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
+{
+    extern __shared__ __align__(16) uint8_t fused_smem[];
+    PoseFusedShared& F = *reinterpret_cast<PoseFusedShared*>(fused_smem);
+    EpnpShared& S = *reinterpret_cast<EpnpShared*>(fused_smem + ((sizeof(PoseFusedShared) + 15) / 16) * 16);
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* obj = const_cast<float*>(a.obj) + (size_t)b * a.cap * 3;
+    float* img = const_cast<float*>(a.img) + (size_t)b * a.cap * 2;
+    uint8_t* mask = a.mask + (size_t)b * a.cap;
+    int* inl = a.inliers + (size_t)b * a.cap;
+    int* orig = io.c_orig ? io.c_orig + (size_t)b * a.cap : nullptr;
+
+    // ---- 1. status == 1 landmarks, in order (what `matched_pts[tracked]` does in the reference, :282-284) ----
+    if (tid == 0) F.base = 0;
+    __syncthreads();
+    if (io.lm_status) {
+        const int n = min(max(io.n_lm[b], 0), a.cap);   // a count beyond the slot capacity must not reach the neighbour's arrays
+        for (int base = 0; base < n; base += FUSED_T) {
+            const int i = base + tid;
+            const size_t gi = (size_t)b * a.cap + i;
+            const bool keep = i < n && io.lm_status[gi] == 1;
+            const unsigned bm = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) F.warp_n[warp] = __popc(bm);
+            __syncthreads();
+            int off = F.base;
+            for (int w = 0; w < warp; ++w) off += F.warp_n[w];
+            if (keep) {
+                const int o = off + __popc(bm & ((1u << lane) - 1));
+                obj[3 * o] = io.lm_obj[3 * gi]; obj[3 * o + 1] = io.lm_obj[3 * gi + 1]; obj[3 * o + 2] = io.lm_obj[3 * gi + 2];
+                img[2 * o] = io.lm_next[2 * gi]; img[2 * o + 1] = io.lm_next[2 * gi + 1];
+                orig[o] = i;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < FUSED_T / 32; ++w) tot += F.warp_n[w];
+                F.base += tot;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) const_cast<int*>(a.n)[b] = F.base;
+    }
+    const int N = io.lm_status ? F.base : min(max(a.n[b], 0), a.cap);
+    if (tid == 0) {
+        F.niters = N == 4 ? 1 : (N > 4 ? (a.iters > 1 ? a.iters : 1) : 0);
+        F.max_good = 0; F.win = -1; F.it0 = 0; F.pos = 0;
+    }
+    __syncthreads();
+
+    // ---- 2. RANSAC in chunks of 32 hypotheses; thread 0 replays cv2's loop after each chunk ----
+    while (F.it0 < F.niters) {                       // block-uniform: both change only between barriers
+        const int it0 = F.it0;
+        const int nh = min(FUSED_CHUNK, F.niters - it0);
+        if (warp == 0) {
+            if (N == 4) { if (lane < 4) F.smp[lane] = lane; }   // count == modelPoints: one direct solve on all points
+            else fused_draw_samples(a, F, b, N, nh, lane);
+        }
+        if (tid < FUSED_CHUNK) F.cnt[tid] = 0;
+        __syncthreads();
+        // one hypothesis per thread, spread over the warps (P3P branches diverge: 4 per warp, 8 warps issue in parallel)
+        if ((tid & 7) == 0) {
+            const int h = tid >> 3;
+            int okh = 0;
+            if (h < nh && F.smp[4 * h] >= 0) okh = pnp_solve_one(a, obj, img, F.smp + 4 * h, F.h + 12 * h, F.rv + 3 * h);
+            F.ok[h] = okh;
+        }
+        __syncthreads();
+        if (N > 4) {
+            for (int base = 0; base < N; base += FUSED_T) {
+                const int i = base + tid;
+                const bool live = i < N;
+                double X = 0, Y = 0, Z = 0;
+                float iu = 0, iv = 0;
+                if (live) { X = obj[3 * i]; Y = obj[3 * i + 1]; Z = obj[3 * i + 2]; iu = img[2 * i]; iv = img[2 * i + 1]; }
+                for (int h = 0; h < nh; ++h) {
+                    if (!F.ok[h]) continue;   // block-uniform
+                    const bool in = live && pnp_is_inlier(F.h + h * 12, a.fx, a.fy, a.cx, a.cy, X, Y, Z, iu, iv, a.thr_sq);
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (lane == 0 && m) atomicAdd(&F.cnt[h], __popc(m));
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            int niters = F.niters, max_good = F.max_good, win = F.win;
+            if (N == 4) { win = F.ok[0] ? 0 : -1; if (win == 0) { for (int k = 0; k < 12; ++k) F.win_h[k] = F.h[k]; for (int k = 0; k < 3; ++k) F.win_rv[k] = F.rv[k]; } }
+            else {
+                for (int h = 0; h < nh && it0 + h < niters; ++h) {
+                    if (!F.ok[h]) continue;
+                    const int good = F.cnt[h];
+                    if (good > (max_good > 3 ? max_good : 3)) {
+                        win = it0 + h; max_good = good;
+                        niters = ransac_update_num_iters(a.conf, (double)(N - good) / N, 4, niters);
+                        for (int k = 0; k < 12; ++k) F.win_h[k] = F.h[12 * h + k];
+                        for (int k = 0; k < 3; ++k) F.win_rv[k] = F.rv[3 * h + k];
+                    }
+                }
+            }
+            F.niters = niters; F.max_good = max_good; F.win = win; F.it0 = it0 + nh;
+        }
+        __syncthreads();
+    }
+
+    // ---- 3. winner mask + ordered inlier list ----
+    const int win = F.win;
+    int M = 0;
+    if (tid == 0) { a.winner[b] = win; a.iters_run[b] = F.niters; F.base = 0; }
+    __syncthreads();
+    if (win < 0) {
+        for (int i = tid; i < a.cap; i += FUSED_T) mask[i] = 0;
+        if (tid == 0) { a.n_inliers[b] = 0; a.ok[b] = 0; }
+    } else {
+        for (int base = 0; base < a.cap; base += FUSED_T) {
+            const int i = base + tid;
+            bool in = false;
+            if (i < N) in = N == 4 ? true : pnp_is_inlier(F.win_h, a.fx, a.fy, a.cx, a.cy, obj[3 * i], obj[3 * i + 1], obj[3 * i + 2], img[2 * i], img[2 * i + 1], a.thr_sq);
+            const unsigned bm = __ballot_sync(0xffffffffu, in);
+            if (lane == 0) F.warp_n[warp] = __popc(bm);
+            __syncthreads();
+            int off = F.base;
+            for (int w = 0; w < warp; ++w) off += F.warp_n[w];
+            if (in) inl[off + __popc(bm & ((1u << lane) - 1))] = i;
+            if (i < a.cap) mask[i] = in ? 1 : 0;
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < FUSED_T / 32; ++w) tot += F.warp_n[w];
+                F.base += tot;
+            }
+            __syncthreads();
+        }
+        M = F.base;
+        double* pose = a.pose + (size_t)b * 6;
+        if (tid == 0) {
+            a.n_inliers[b] = M; a.ok[b] = 1;
+            // RANSAC model (what cv2 falls back to / returns for N == 4)
+            pose[0] = F.win_rv[0]; pose[1] = F.win_rv[1]; pose[2] = F.win_rv[2];
+            pose[3] = F.win_h[9]; pose[4] = F.win_h[10]; pose[5] = F.win_h[11];
+        }
+        __syncthreads();
+        // ---- 4. EPnP refit on the inliers (N == 4: cv2 returns the direct P3P solve) ----
+        if (N != 4 && M >= 4) epnp_block(a, S, obj, img, inl, M, pose);
+    }
+    // ---- 5. inlier mask over the ORIGINAL landmark slots (:346) ----
+    if (io.mask_out) {
+        __syncthreads();
+        uint8_t* mo = io.mask_out + (size_t)b * a.cap;
+        for (int i = tid; i < a.cap; i += FUSED_T) mo[i] = 0;
+        __syncthreads();
+        for (int k = tid; k < M; k += FUSED_T) mo[orig[inl[k]]] = 1;
+        if (tid == 0) { io.n_inl_out[b] = M; io.ok_out[b] = win >= 0 ? 1 : 0; }
     }
 }
 
@@ -692,9 +983,33 @@ void vo_pnp_carve_workspace(PnpArgs& a, void* ws)
     a.ok_ws = (uint8_t*)take((size_t)a.batch * sizeof(int));
 }
 
+bool vo_pnp_fused_ok(const PnpArgs& a, bool gen_samples)
+{
+    static const bool off = getenv("B200VO_POSE_UNFUSED") != nullptr;   // A/B switch for measurements
+    return !off && gen_samples && !a.full_counts && a.cap <= VO_PNP_FUSED_MAX_N;
+}
+
+int vo_pnp_fused_launch(b200vo_ctx* ctx, const PnpArgs& a, const PoseBatchIO& io)
+{
+    if (a.batch <= 0) return 0;
+    const size_t smem = ((sizeof(PoseFusedShared) + 15) / 16) * 16 + sizeof(EpnpShared);
+    static_assert(((sizeof(PoseFusedShared) + 15) / 16) * 16 + sizeof(EpnpShared) <= 48 * 1024, "static limit of dynamic shared memory");
+    // few sequences: the chain's latency is the step (single sequence, small shards) -> the unconstrained build;
+    // many: it runs beside the candidate tracker and must leave it registers -> two CTAs per SM
+    static const char* force = getenv("B200VO_POSE_REGS");   // "255" / "128": A/B switch for measurements
+    const bool wide = force ? atoi(force) > 128 : 2 * a.batch <= ctx->num_sms;
+    VO_CUDA(ctx, cudaMemsetAsync(a.flags, 0, (size_t)a.batch * 3 * sizeof(int), ctx->stream));
+    if (wide) pnp_fused_kernel<1><<<a.batch, FUSED_T, smem, ctx->stream>>>(a, io);
+    else pnp_fused_kernel<2><<<a.batch, FUSED_T, smem, ctx->stream>>>(a, io);
+    ctx->launches++;
+    VO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
 int vo_pnp_launch(b200vo_ctx* ctx, const PnpArgs& a, bool gen_samples)
 {
     if (a.batch <= 0) return 0;
+    if (vo_pnp_fused_ok(a, gen_samples)) return vo_pnp_fused_launch(ctx, a, PoseBatchIO{});
     VO_CUDA(ctx, cudaMemsetAsync(a.flags, 0, (size_t)a.batch * 3 * sizeof(int), ctx->stream));
     if (gen_samples) {
         const size_t smem = (size_t)a.n_raw * sizeof(int);

@@ -38,7 +38,24 @@ struct PnpArgs {
     uint8_t* ok;            // [batch]
 };
 
+// What the batched per-frame step adds around the RANSAC when the whole pose chain runs as ONE kernel
+// (pnp_fused_kernel): the status==1 compaction in front (PnpArgs::obj/img/n are then OUTPUTS of the kernel) and the
+// inlier mask over the original landmark slots behind.  All null: the correspondences are already compact.
+struct PoseBatchIO {
+    const int* n_lm = nullptr;            // [batch] live landmark slots
+    const float* lm_next = nullptr;       // [batch][cap][2] tracked positions
+    const uint8_t* lm_status = nullptr;   // [batch][cap]
+    const float* lm_obj = nullptr;        // [batch][cap][3]
+    int* c_orig = nullptr;                // [batch][cap] original slot of each compacted correspondence
+    uint8_t* mask_out = nullptr;          // [batch][cap] inlier mask over the original slots
+    int* n_inl_out = nullptr;             // [batch]
+    uint8_t* ok_out = nullptr;            // [batch]
+};
+#define VO_PNP_FUSED_MAX_N 4096   // correspondences per sequence up to which one CTA runs the whole chain
+
 void vo_rng_raw_stream(uint32_t* out, int n);
+bool vo_pnp_fused_ok(const PnpArgs& a, bool gen_samples);
+int vo_pnp_fused_launch(b200vo_ctx* ctx, const PnpArgs& a, const PoseBatchIO& io);
 size_t vo_pnp_workspace_bytes(int batch, int cap, int iters);
 void vo_pnp_carve_workspace(PnpArgs& a, void* ws);
 int vo_pnp_launch(b200vo_ctx* ctx, const PnpArgs& a, bool gen_samples);

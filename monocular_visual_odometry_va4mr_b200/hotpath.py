@@ -74,3 +74,29 @@ def triangulate_landmarks(K, options, potential_first_keys, potential_keys, pote
             _p(fp, c_i32p), n, _p(poses, c_f64p), len(poses), _p(cur, c_f64p), _p(keep, c_u8p), _p(lm, c_f32p), _p(kp, c_f32p),
             C.byref(cnt)), "b200vo_triangulate_landmarks")
     return keep.astype(bool), lm[:cnt.value].copy(), kp[:cnt.value].copy()
+
+
+def find_essential_mat_samples(p1, p2, K, samples, prob=0.999, threshold=1.0, want_models=False,
+                               ctx: _lib.Context | None = None):
+    """``cv2.findEssentialMat(p1, p2, K, RANSAC, prob, threshold)`` (ref :308) on the CALLER's 5-subsets
+    (``samples`` int32 (iters,5)): the same-hypothesis-set form north_star's mask criterion is stated for.
+    Returns a dict: E (3,3)|None, mask (n,1) uint8|None, nmodels int32 (iters,), counts int32 (iters,10),
+    models float64 (iters,10,3,3)|None, winner (sample*10+model, -1: none), iters_run."""
+    ctx = ctx or _lib.default_context(0)
+    p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+    Kf = np.ascontiguousarray(K, np.float64).reshape(9)
+    smp = np.ascontiguousarray(samples, np.int32).reshape(-1, 5)
+    n, iters = len(p1), len(smp)
+    E = np.zeros(9)
+    mask = np.zeros((n, 1), np.uint8)
+    nmodels = np.zeros(iters, np.int32)
+    counts = np.zeros((iters, 10), np.int32)
+    models = np.zeros((iters, 10, 3, 3)) if want_models else None
+    found, winner, run = C.c_int(0), C.c_int(-1), C.c_int(0)
+    _chk(ctx, ctx.lib.b200vo_find_essential_mat_ransac_samples(
+        ctx.h, _p(p1, c_f32p), _p(p2, c_f32p), n, _p(Kf, c_f64p), _p(smp, c_i32p), iters, float(prob), float(threshold),
+        _p(E, c_f64p), _p(mask, c_u8p), C.byref(found), _p(nmodels, c_i32p), _p(counts, c_i32p),
+        _p(models, c_f64p) if want_models else None, C.byref(winner), C.byref(run)), "b200vo_find_essential_mat_ransac_samples")
+    return dict(E=E.reshape(3, 3) if found.value else None, mask=mask if found.value else None, nmodels=nmodels, counts=counts,
+                models=models, winner=winner.value, iters_run=run.value)

@@ -2,6 +2,7 @@
 
   python profiles/summarize.py launches gpurun_out/launches_r1.csv > profiles/r1_launches_summary.txt
   python profiles/summarize.py kernel gpurun_out/klt_r1.ncu-rep   > profiles/r1_klt_kernel_full.txt
+  python profiles/summarize.py source gpurun_out/r2a_klt.ncu-rep  > profiles/r2a_klt_source_hot.txt   (needs -lineinfo + --import-source on)
 """
 import collections
 import csv
@@ -55,5 +56,42 @@ def kernel(path):
             print(f"{k} = {v}")
 
 
+def source(path, top=45):
+    """Per SOURCE LINE: share of executed warp instructions, shared-memory wavefronts (actual / ideal) and stall samples."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    recs, cur, hdr, kname = [], None, None, "?"
+    for r in rows:
+        if r and r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+        elif r and r[0] == "Function Name":
+            kname = r[1]
+        elif r and r[0] == "Line No":
+            hdr = r
+        elif hdr and r and r[0].isdigit():
+            recs.append((cur, int(r[0]), r[1].strip(), dict(zip(hdr, r))))
+
+    def num(x):
+        try:
+            return float(x)
+        except (TypeError, ValueError):
+            return 0.0
+    ti = sum(num(d["Instructions Executed"]) for *_, d in recs) or 1.0
+    ts = sum(num(d["# Samples"]) for *_, d in recs) or 1.0
+    tw = sum(num(d["L1 Wavefronts Shared"]) for *_, d in recs)
+    te = sum(num(d["L1 Wavefronts Shared Excessive"]) for *_, d in recs)
+    print(f"# {path}: {kname}: per source line (ncu --set full --import-source on; compiled with -lineinfo)")
+    print(f"# warp instructions executed {ti:.0f}; shared-memory wavefronts {tw:.0f} of which excessive (bank conflicts) {te:.0f} = {100 * te / max(tw, 1):.1f} %")
+    print("# -- by instructions executed")
+    for f, l, src, d in sorted(recs, key=lambda o: -num(o[3]["Instructions Executed"]))[:top]:
+        print(f"{f}:{l:<4d} inst {100 * num(d['Instructions Executed']) / ti:5.2f} %  samples {100 * num(d['# Samples']) / ts:5.2f} %  | {src[:120]}")
+    print("# -- by shared-memory wavefronts")
+    for f, l, src, d in sorted(recs, key=lambda o: -num(o[3]["L1 Wavefronts Shared"]))[:16]:
+        if num(d["L1 Wavefronts Shared"]) <= 0:
+            break
+        print(f"{f}:{l:<4d} wavefronts {num(d['L1 Wavefronts Shared']) / 1e6:7.2f} M  ideal {num(d['L1 Wavefronts Shared Ideal']) / 1e6:7.2f} M  "
+              f"excessive {num(d['L1 Wavefronts Shared Excessive']) / 1e6:7.2f} M  | {src[:100]}")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "source": source}[sys.argv[1]](sys.argv[2])

@@ -68,3 +68,50 @@ def test_reference_call_pattern_and_edges():
         cv2_compat.findEssentialMat(p1, p2, K, method=cv2_compat.LMEDS)
     with pytest.raises(cv2_compat.error):
         cv2_compat.findEssentialMat(p1, p2[:-1], K, method=cv2_compat.RANSAC)
+
+
+def test_same_sample_set_counts_and_mask_equal_the_oracle():
+    """north_star: "RANSAC inlier masks must be bit-exact given the same hypothesis sample set".  The GPU solver and the
+    oracle's get the SAME 5-subsets; per-sample model counts, per-(sample, model) inlier counts, the winner of cv2's
+    sequential loop and the mask must agree.  A count may differ only where a point's Sampson error lies within the two
+    solvers' agreement (1e-12 relative) of the threshold; the test lists and bounds such borderline points."""
+    import oracle
+    from make_golden import make_emat_pair
+    from monocular_visual_odometry_va4mr_b200 import hotpath
+    borderline_total = 0
+    for n, of, seed, iters in ((1500, 0.3, 50, 160), (600, 0.55, 51, 256), (3000, 0.15, 52, 96)):
+        p1, p2, K = make_emat_pair(n, of, seed)
+        smp = oracle.ransac_subsets(n, 5, iters)
+        out = hotpath.find_essential_mat_samples(p1, p2, K, smp, prob=0.99, threshold=1.0, want_models=True)
+        n1 = np.column_stack([(p1[:, 0].astype(np.float64) - K[0, 2]) / K[0, 0], (p1[:, 1].astype(np.float64) - K[1, 2]) / K[1, 1]])
+        n2 = np.column_stack([(p2[:, 0].astype(np.float64) - K[0, 2]) / K[0, 0], (p2[:, 1].astype(np.float64) - K[1, 2]) / K[1, 1]])
+        t = 1.0 / ((K[0, 0] + K[1, 1]) / 2)
+        thr = np.float32(t * t)
+        o_nm = np.zeros(iters, np.int32)
+        o_cnt = np.zeros((iters, 10), np.int32)
+        for i in range(iters):
+            Es = oracle.five_point(n1[smp[i]], n2[smp[i]])
+            o_nm[i] = len(Es)
+            for m, Em in enumerate(Es):
+                err = oracle.sampson_errors(n1, n2, Em)
+                o_cnt[i, m] = int((err <= thr).sum())
+                if out["counts"][i, m] != o_cnt[i, m]:
+                    # the two solvers' E agree to ~1e-13: only a point whose error sits on the threshold may flip
+                    g_err = oracle.sampson_errors(n1, n2, out["models"][i, m])
+                    flipped = (err <= thr) != (g_err <= thr)
+                    assert flipped.sum() == abs(int(out["counts"][i, m]) - int(o_cnt[i, m]))
+                    assert np.all(np.abs(err[flipped].astype(np.float64) - float(thr)) <= 1e-6 * float(thr))
+                    borderline_total += int(flipped.sum())
+        assert np.array_equal(out["nmodels"], o_nm)
+        assert np.abs(out["counts"] - o_cnt).max() <= 1
+        # cv2's loop on the GPU's own counts: the winner and the number of iterations it runs
+        best, run = oracle.ransac_select(out["counts"], out["nmodels"], 10, iters, n, 5, 0.99)
+        assert best == out["winner"] and run == out["iters_run"]
+        # and the mask is the winner's inlier set
+        wi, wm = divmod(out["winner"], 10)
+        want = (oracle.sampson_errors(n1, n2, out["models"][wi, wm]) <= thr).astype(np.uint8)
+        assert np.array_equal(out["mask"].ravel(), want)
+        if np.array_equal(out["counts"], o_cnt):     # no borderline point in this case: everything is identical to the oracle's run
+            ob, _ = oracle.ransac_select(o_cnt, o_nm, 10, iters, n, 5, 0.99)
+            assert ob == out["winner"]
+    assert borderline_total <= 2

@@ -70,6 +70,26 @@ def test_full_size_properties():
     assert np.array_equal(dist[rows, 1], np.sqrt(d2.min(1).astype(np.float32)))
 
 
+def test_full_size_8192_vs_live_cv2_every_row():
+    """BASELINE config 3 as stated: 8192 x 8192 descriptors, ALL rows against cv2's own BFMatcher (79 ms on the host)
+    and against the C oracle: indices, distances and accept flags bit-exact."""
+    import oracle
+    from make_golden import sift_like
+    q, t = sift_like(8192, 21), sift_like(8192, 22)
+    t[100] = q[5]; t[4000] = q[5]            # planted ties: the lower train index must win
+    t[8191] = q[8191]
+    idx, dist, acc = cv2_compat.knn2_ratio(q, t, 0.8)
+    oi, od, oa = oracle.knn2_ratio(q, t, 0.8)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od) and np.array_equal(acc, oa)
+    assert tuple(idx[5]) == (100, 4000) and idx[8191, 0] == 8191
+    cv2 = pytest.importorskip("cv2")
+    m = cv2.BFMatcher().knnMatch(q, t, k=2)
+    ci = np.array([[a.trainIdx, b.trainIdx] for a, b in m], np.int32)
+    cd = np.array([[a.distance, b.distance] for a, b in m], np.float32)
+    ca = np.array([a.distance < 0.8 * b.distance for a, b in m], np.uint8)      # the reference's ratio loop (:218-224)
+    assert np.array_equal(idx, ci) and np.array_equal(dist, cd) and np.array_equal(acc, ca)
+
+
 def test_errors():
     from make_golden import sift_like
     q = sift_like(10, 1)
