@@ -108,6 +108,38 @@ int b200vo_find_essential_mat_ransac_samples(b200vo_ctx* ctx, const float* p1, c
                                              double* models_out, int* winner_out, int* iters_run);
 
 /*
+ * ---- device-pointer forms of the five call sites (SURVEY.md 8b "_dev") ----
+ * Same arguments with every array already resident in DEVICE memory (e.g. torch data_ptr()) and the
+ * results left there; asynchronous on the ctx stream (b200vo_stream / b200vo_sync).  The counts that
+ * the host forms return by value come back as one-element device arrays.
+ */
+int b200vo_calc_optical_flow_pyr_lk_dev(b200vo_ctx* ctx, const uint8_t* prev_dev, const uint8_t* next_dev,
+                                        int rows, int cols, size_t prev_step, size_t next_step,
+                                        const float* prev_pts_dev, int n, int win_w, int win_h,
+                                        int max_level, int crit_type, int crit_max_count,
+                                        double crit_eps, int flags, double min_eig_thr,
+                                        float* next_pts_dev, uint8_t* status_dev, float* err_dev);
+/* corners_dev float32 (max_corners,2); n_out_dev int32[1] (-1: more than 32768 candidates above the
+ * quality threshold -- use the host form).  Needs minDistance >= 1 and maxCorners > 0. */
+int b200vo_good_features_to_track_dev(b200vo_ctx* ctx, const uint8_t* img_dev, int rows, int cols,
+                                      size_t step, int max_corners, double quality, double min_dist,
+                                      int block_size, float* corners_dev, int32_t* n_out_dev);
+/* bad_dev (may be NULL) int32[1]: 1 when a descriptor is not integer-valued in 0..255. */
+int b200vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* t_dev, int nt,
+                          int dim, double ratio, int32_t* idx2_dev, float* dist2_dev,
+                          uint8_t* accept_dev, int32_t* bad_dev);
+/* E_dev double[9], mask_dev uint8 (n), found_dev int32[1]. */
+int b200vo_find_essential_mat_ransac_dev(b200vo_ctx* ctx, const float* p1_dev, const float* p2_dev,
+                                         int n, const double K[9], double prob, double thr,
+                                         int max_iters, double* E_dev, uint8_t* mask_dev,
+                                         int32_t* found_dev);
+/* pose_dev double[6] = rvec | tvec, inliers_dev int32 (n), n_inliers_dev int32[1], success_dev uint8[1]. */
+int b200vo_solve_pnp_ransac_p3p_dev(b200vo_ctx* ctx, const float* obj_dev, const float* img_dev, int n,
+                                    const double K[9], int iters, float reproj_err, double conf,
+                                    double* pose_dev, int32_t* inliers_dev, int32_t* n_inliers_dev,
+                                    uint8_t* success_dev);
+
+/*
  * ---- components next to the hot path ----
  *
  * Replaces the candidate min-distance filter of feature_adding at :258

@@ -60,6 +60,19 @@ SIGNATURES = {
     "b200vo_find_essential_mat_ransac_samples": (C.c_int, [
         C.c_void_p, c_f32p, c_f32p, C.c_int, c_f64p, c_i32p, C.c_int, C.c_double, C.c_double, c_f64p, c_u8p, c_intp,
         c_i32p, c_i32p, c_f64p, c_intp, c_intp]),
+    # device-pointer forms: every array argument is a raw device address (int)
+    "b200vo_calc_optical_flow_pyr_lk_dev": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int,
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200vo_good_features_to_track_dev": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    "b200vo_knn2_ratio_dev": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200vo_find_essential_mat_ransac_dev": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200vo_solve_pnp_ransac_p3p_dev": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p, C.c_int, C.c_float, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p]),
     "b200vo_recover_pose": (C.c_int, [C.c_void_p, c_f64p, c_f32p, c_f32p, C.c_int, c_f64p, C.c_double, c_f64p, c_f64p, c_u8p, c_intp]),
     "b200vo_min_distance_mask": (C.c_int, [C.c_void_p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_float, c_u8p]),
     "b200vo_triangulate_landmarks": (C.c_int, [

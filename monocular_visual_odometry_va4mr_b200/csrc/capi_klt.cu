@@ -115,6 +115,52 @@ extern "C" int b200vo_calc_optical_flow_pyr_lk(b200vo_ctx* ctx, const uint8_t* p
     return klt_on_slots(ctx, s0, s1, prev_pts, n, kp, max_level, next_pts, status, err, pin_off);
 }
 
+// pyramid of a DEVICE-resident image into an internal slot (no host staging)
+static int build_slot_from_device(b200vo_ctx* ctx, int slot, int stage_idx, const uint8_t* img_dev, int rows, int cols, size_t step,
+                                  int win_w, int win_h, int max_level)
+{
+    FrameSlot& fs = ctx->slots[slot];
+    const int levels = vo_pyr_levels(cols, rows, win_w, win_h, max_level);
+    PyrGeom g;
+    vo_pyr_geom(rows, cols, levels, &g);
+    VO_TRY(vo_reserve(ctx, fs.slab, g.slab_bytes));
+    const size_t raw_bytes = (size_t)rows * cols;
+    const uint8_t* raw = img_dev;
+    if (step != (size_t)cols) {     // pitched view: pack the rows first
+        VO_TRY(vo_reserve(ctx, ctx->d_stage_img[stage_idx], raw_bytes));
+        VO_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage_img[stage_idx].p, (size_t)cols, img_dev, step, (size_t)cols, (size_t)rows,
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+        raw = (const uint8_t*)ctx->d_stage_img[stage_idx].p;
+    }
+    VO_TRY(vo_build_pyramids(ctx, raw, raw_bytes, rows, cols, g, (uint8_t*)fs.slab.p, g.slab_bytes, 1));
+    fs.geom = g; fs.rows = rows; fs.cols = cols; fs.valid = true;
+    return 0;
+}
+
+// Device-pointer form of b200vo_calc_optical_flow_pyr_lk (SURVEY 8b `_dev`): images, points and results stay in device
+// memory; asynchronous on the ctx stream (pair with b200vo_sync).
+extern "C" int b200vo_calc_optical_flow_pyr_lk_dev(b200vo_ctx* ctx, const uint8_t* prev_dev, const uint8_t* next_dev, int rows, int cols,
+                                                   size_t prev_step, size_t next_step, const float* prev_pts_dev, int n, int win_w,
+                                                   int win_h, int max_level, int crit_type, int crit_max_count, double crit_eps,
+                                                   int flags, double min_eig_thr, float* next_pts_dev, uint8_t* status_dev,
+                                                   float* err_dev)
+{
+    VO_TRY(klt_check_args(ctx, rows, cols, win_w, win_h, max_level, flags));
+    if (!prev_dev || !next_dev || (n > 0 && (!prev_pts_dev || !next_pts_dev || !status_dev)))
+        return vo_set_err(ctx, B200VO_E_BADARG, "null pointer");
+    if (n < 0) return vo_set_err(ctx, B200VO_E_BADARG, "npoints >= 0");
+    if (prev_step < (size_t)cols || next_step < (size_t)cols) return vo_set_err(ctx, B200VO_E_BADARG, "step < cols");
+    if (n == 0) return 0;
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int s0 = B200VO_MAX_SLOTS, s1 = B200VO_MAX_SLOTS + 1;  // internal slots
+    VO_TRY(build_slot_from_device(ctx, s0, 0, prev_dev, rows, cols, prev_step, win_w, win_h, max_level));
+    VO_TRY(build_slot_from_device(ctx, s1, 1, next_dev, rows, cols, next_step, win_w, win_h, max_level));
+    const KltParams kp = make_params(win_w, win_h, crit_type, crit_max_count, crit_eps, min_eig_thr);
+    const FrameSlot& fp = ctx->slots[s0];
+    return vo_klt_launch(ctx, fp.geom, (const uint8_t*)fp.slab.p, 0, (const uint8_t*)ctx->slots[s1].slab.p, 0, 1, n, nullptr, n,
+                         prev_pts_dev, next_pts_dev, status_dev, err_dev, kp);
+}
+
 extern "C" int b200vo_frame_upload(b200vo_ctx* ctx, int slot, const uint8_t* img, int rows, int cols,
                                    size_t step, int win_w, int win_h, int max_level)
 {

@@ -97,3 +97,44 @@ extern "C" int b200vo_solve_pnp_ransac_p3p_samples(b200vo_ctx* ctx, const float*
     return pnp_run(ctx, obj, img, n, K, samples, iters, reproj_err, conf, rvec, tvec, inliers, n_inliers, success,
                    counts_out, winner_iter, iters_run);
 }
+
+// Device-pointer form (SURVEY 8b `_dev`): obj_dev float32 (n,3), img_dev float32 (n,2) in device memory; pose_dev double[6]
+// (rvec | tvec), inliers_dev int32 (n) ascending, n_inliers_dev int32[1], success_dev uint8[1] are written on the device.
+// Asynchronous on the ctx stream.
+__global__ void pnp_export_kernel(const int* __restrict__ n_inl, const uint8_t* __restrict__ ok, int32_t* __restrict__ n_out)
+{
+    *n_out = *ok ? *n_inl : 0;
+}
+
+extern "C" int b200vo_solve_pnp_ransac_p3p_dev(b200vo_ctx* ctx, const float* obj_dev, const float* img_dev, int n, const double K[9],
+                                               int iters, float reproj_err, double conf, double* pose_dev, int32_t* inliers_dev,
+                                               int32_t* n_inliers_dev, uint8_t* success_dev)
+{
+    if (!ctx) return B200VO_E_BADARG;
+    if (!obj_dev || !img_dev || !K || !pose_dev || !inliers_dev || !n_inliers_dev || !success_dev)
+        return vo_set_err(ctx, B200VO_E_BADARG, "null pointer");
+    if (n < 4)  // cv2: solvepnp.cpp CV_Assert(npoints >= 4 && ...)
+        return vo_set_err(ctx, B200VO_E_BADARG, "npoints >= 4 && npoints == std::max(ipoints.checkVector(2, CV_32F), ipoints.checkVector(2, CV_64F))");
+    if (iters < 1) iters = 1;
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PnpArgs a{};
+    a.batch = 1; a.cap = n; a.iters = iters;
+    a.fx = K[0]; a.fy = K[4]; a.cx = K[2]; a.cy = K[5];
+    a.thr_sq = (float)((double)reproj_err * (double)reproj_err);
+    a.conf = conf;
+    a.n_raw = 8 * iters + 256;
+    VO_TRY(vo_rng_table(ctx, a.n_raw, &a.rng_raw));
+    const size_t b_mask = vo_align((size_t)n, 256), b_ws = vo_pnp_workspace_bytes(1, n, iters);
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[1], 256 + b_mask + b_ws));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[1].p;
+    a.obj = obj_dev; a.img = img_dev; a.n = (const int*)d;
+    a.mask = d + 256;
+    a.inliers = inliers_dev; a.pose = pose_dev; a.ok = success_dev;
+    vo_pnp_carve_workspace(a, d + 256 + b_mask);
+    VO_CUDA(ctx, cudaMemcpyAsync(d, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));   // pageable source: staged before the call returns
+    VO_TRY(vo_pnp_launch(ctx, a, true));
+    pnp_export_kernel<<<1, 1, 0, ctx->stream>>>(a.n_inliers, a.ok, n_inliers_dev);
+    ctx->launches++;
+    VO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}

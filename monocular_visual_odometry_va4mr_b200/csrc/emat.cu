@@ -513,14 +513,29 @@ emat_finish_kernel(EmatArgs a)
 
 int vo_rng_table(b200vo_ctx* ctx, int n, const uint32_t** d_table);
 
+// dev_io != nullptr: p1 / p2 are DEVICE pointers and the results go to dev_io (device) instead of E / mask / found
+struct EmatDevIO { double* E; uint8_t* mask; int32_t* found; };
+
+__global__ void emat_export_kernel(EmatArgs a, EmatDevIO io)
+{
+    const int ok = a.result[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) io.mask[i] = ok ? a.mask[i] : 0;
+    if (blockIdx.x == 0 && threadIdx.x < 9) io.E[threadIdx.x] = ok ? a.E[threadIdx.x] : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *io.found = ok;
+}
+
 static int emat_run(b200vo_ctx* ctx, const float* p1, const float* p2, int n, const double K[9], const int32_t* samples,
                     double prob, double thr, int max_iters, double E[9], uint8_t* mask, int* found, int32_t* nmodels_out,
-                    int32_t* counts_out, double* models_out, int* winner_out, int* iters_run)
+                    int32_t* counts_out, double* models_out, int* winner_out, int* iters_run, const EmatDevIO* dev_io = nullptr)
 {
-    if (!ctx || !p1 || !p2 || !K || !E || !mask || !found) return B200VO_E_BADARG;
-    *found = 0;
+    if (!ctx || !p1 || !p2 || !K) return B200VO_E_BADARG;
+    if (!dev_io && (!E || !mask || !found)) return B200VO_E_BADARG;
+    if (found) *found = 0;
     if (n < 0) return vo_set_err(ctx, B200VO_E_BADARG, "npoints >= 0 && points2.checkVector(2) == npoints");
-    if (n < 5) return 0;   // cv2 returns an empty matrix
+    if (n < 5) {   // cv2 returns an empty matrix
+        if (dev_io) { VO_CUDA(ctx, cudaSetDevice(ctx->device)); VO_CUDA(ctx, cudaMemsetAsync(dev_io->found, 0, 4, ctx->stream)); }
+        return 0;
+    }
     VO_CUDA(ctx, cudaSetDevice(ctx->device));
     VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     const int iters = max_iters > 1 ? max_iters : 1;
@@ -553,9 +568,13 @@ static int emat_run(b200vo_ctx* ctx, const float* p1, const float* p2, int n, co
     const size_t b_dbg = samples ? b_s + b_nm + b_c + (models_out ? b_m : 0) : 0;
     VO_TRY(vo_reserve_pinned(ctx, 2 * b_p + b_mask + 1024 + b_dbg));
     uint8_t* hp = (uint8_t*)ctx->h_pin;
-    memcpy(hp, p1, (size_t)n * 8);
-    memcpy(hp + b_p, p2, (size_t)n * 8);
-    VO_CUDA(ctx, cudaMemcpyAsync((void*)a.p1, hp, 2 * b_p, cudaMemcpyHostToDevice, ctx->stream));
+    if (dev_io) {
+        a.p1 = p1; a.p2 = p2;     // already resident
+    } else {
+        memcpy(hp, p1, (size_t)n * 8);
+        memcpy(hp + b_p, p2, (size_t)n * 8);
+        VO_CUDA(ctx, cudaMemcpyAsync((void*)a.p1, hp, 2 * b_p, cudaMemcpyHostToDevice, ctx->stream));
+    }
     VO_CUDA(ctx, cudaMemsetAsync(d_small, 0, 512, ctx->stream));
     int* h_small = (int*)(hp + 2 * b_p + b_mask);
     h_small[0] = n;
@@ -591,6 +610,12 @@ static int emat_run(b200vo_ctx* ctx, const float* p1, const float* p2, int n, co
     emat_finish_kernel<<<1, 256, 0, ctx->stream>>>(a);
     ctx->launches += 1;
     VO_CUDA(ctx, cudaGetLastError());
+    if (dev_io) {   // results stay on the device; nothing to wait for
+        emat_export_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a, *dev_io);
+        ctx->launches += 1;
+        VO_CUDA(ctx, cudaGetLastError());
+        return 0;
+    }
     VO_CUDA(ctx, cudaMemcpyAsync(hp, a.mask, b_mask, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(ctx, cudaMemcpyAsync(hp + b_mask, d_small, 512, cudaMemcpyDeviceToHost, ctx->stream));
     if (samples) {
@@ -636,4 +661,16 @@ extern "C" int b200vo_find_essential_mat_ransac_samples(b200vo_ctx* ctx, const f
     if (!samples || iters < 1) return B200VO_E_BADARG;
     return emat_run(ctx, p1, p2, n, K, samples, prob, thr, iters, E, mask, found, nmodels_out, counts_out, models_out, winner_out,
                     iters_run);
+}
+
+// Device-pointer form (SURVEY 8b `_dev`): p1_dev / p2_dev float32 (n,2) in device memory; E_dev double[9], mask_dev uint8 (n),
+// found_dev int32[1] are written on the device (zeros when nothing was found).  Asynchronous on the ctx stream.
+extern "C" int b200vo_find_essential_mat_ransac_dev(b200vo_ctx* ctx, const float* p1_dev, const float* p2_dev, int n, const double K[9],
+                                                    double prob, double thr, int max_iters, double* E_dev, uint8_t* mask_dev,
+                                                    int32_t* found_dev)
+{
+    if (!E_dev || !mask_dev || !found_dev) return B200VO_E_BADARG;
+    const EmatDevIO io{E_dev, mask_dev, found_dev};
+    return emat_run(ctx, p1_dev, p2_dev, n, K, nullptr, prob, thr, max_iters, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                    nullptr, nullptr, &io);
 }

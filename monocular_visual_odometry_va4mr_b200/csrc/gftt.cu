@@ -709,3 +709,51 @@ int vo_gftt_batch_launch(b200vo_ctx* ctx, const uint8_t* d_img0, size_t img_stri
     *d_small_out = d_small;
     return 0;
 }
+
+// Device-pointer form of b200vo_good_features_to_track (SURVEY 8b `_dev`): the image is already in device memory, the
+// corner list stays there.  Runs the batched pipeline for one image (no intermediate host synchronisation):
+// needs minDistance >= 1, maxCorners > 0 and at most VO_GFTT_BATCH_CAP candidates above the quality threshold.
+// corners_dev float32 (max_corners, 2); n_out_dev int32[1] = corners found, or -1 when the candidate limit was exceeded.
+__global__ void gftt_export_kernel(const float* __restrict__ src, const int* __restrict__ small, int max_corners,
+                                   float* __restrict__ dst, int* __restrict__ n_out)
+{
+    const bool over = small[1] > GFTT_BATCH_CAP;
+    const int n = over ? 0 : small[2];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * max_corners; i += gridDim.x * blockDim.x) dst[i] = i < 2 * n ? src[i] : 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = over ? -1 : n;
+}
+
+extern "C" int b200vo_good_features_to_track_dev(b200vo_ctx* ctx, const uint8_t* img_dev, int rows, int cols, size_t step,
+                                                 int max_corners, double quality, double min_dist, int block_size,
+                                                 float* corners_dev, int32_t* n_out_dev)
+{
+    if (!ctx || !img_dev || !corners_dev || !n_out_dev) return B200VO_E_BADARG;
+    if (!(quality > 0) || min_dist < 0 || max_corners < 0)   // cv2: featureselect.cpp CV_Assert
+        return vo_set_err(ctx, B200VO_E_BADARG, "qualityLevel > 0 && minDistance >= 0 && maxCorners >= 0");
+    if (block_size != 3) return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "blockSize != 3 not implemented (the reference uses 3)");
+    if (step < (size_t)cols) return vo_set_err(ctx, B200VO_E_BADARG, "step < cols");
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    FrameSlot& fs = ctx->slots[B200VO_MAX_SLOTS + 1];
+    PyrGeom g;
+    vo_pyr_geom(rows, cols, 1, &g);
+    VO_TRY(vo_reserve(ctx, fs.slab, g.slab_bytes));
+    fs.valid = false;
+    const size_t npx = (size_t)rows * cols;
+    const uint8_t* raw = img_dev;
+    if (step != (size_t)cols) {
+        VO_TRY(vo_reserve(ctx, ctx->d_stage_img[1], npx));
+        VO_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage_img[1].p, (size_t)cols, img_dev, step, (size_t)cols, (size_t)rows,
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+        raw = (const uint8_t*)ctx->d_stage_img[1].p;
+    }
+    VO_TRY(vo_build_pyramids(ctx, raw, npx, rows, cols, g, (uint8_t*)fs.slab.p, g.slab_bytes, 1));
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[2], vo_gftt_batch_workspace(rows, cols, 1, max_corners > 0 ? max_corners : 1)));
+    float* d_out = nullptr;
+    int* d_small = nullptr;
+    VO_TRY(vo_gftt_batch_launch(ctx, (const uint8_t*)fs.slab.p + g.off[0], g.slab_bytes, g.pitch[0], rows, cols, 1, max_corners, quality,
+                                min_dist, ctx->d_scratch[2].p, &d_out, &d_small));
+    gftt_export_kernel<<<(2 * max_corners + 255) / 256, 256, 0, ctx->stream>>>(d_out, d_small, max_corners, corners_dev, n_out_dev);
+    ctx->launches++;
+    VO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}

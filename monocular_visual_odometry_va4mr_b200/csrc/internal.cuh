@@ -62,6 +62,7 @@ struct b200vo_ctx {
     size_t h_pin_cap = 0;
     DevBuf d_scratch[8];     // generic device scratch (per-API use)
     FrameSlot slots[B200VO_MAX_SLOTS + 2];  // +2 internal slots for the stateless cv2-style call
+    int* knn_bad_flag = nullptr;   // device flag of the last kNN call (inside d_scratch[3])
     DevBuf d_klt_queue;      // ring of work-queue counters for the persistent tracker kernel
     unsigned klt_queue_next = 0;
     DevBuf d_rng;            // raw cv::RNG stream (uint32)

@@ -321,6 +321,7 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
     float* tn = (float*)d; d += b_tn;
     KnnPartial* part = (KnnPartial*)d; d += b_part;
     int* bad = (int*)d;
+    ctx->knn_bad_flag = bad;
     VO_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
     knn_prep_kernel<<<(nq_pad + 7) / 8, 256, 0, ctx->stream>>>(q_dev, nq, nq_pad, q16, qn, 0.f, bad);
     knn_prep_kernel<<<(nt_pad + 7) / 8, 256, 0, ctx->stream>>>(t_dev, nt, nt_pad, t16, tn, KNN_BIG, bad);
@@ -335,6 +336,41 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
     ctx->launches += 2;
     VO_CUDA(ctx, cudaGetLastError());
     if (bad_flag_host) VO_CUDA(ctx, cudaMemcpyAsync(bad_flag_host, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+// Device-pointer form (SURVEY 8b `_dev`): descriptors already in device memory, results left there; asynchronous on
+// the ctx stream.  bad_dev (may be NULL) int32[1]: 1 when a descriptor is not integer-valued in 0..255.
+__global__ void knn_export_flag_kernel(const int* __restrict__ bad, int32_t* __restrict__ out) { *out = *bad ? 1 : 0; }
+__global__ void knn_empty_train_kernel(int nq, int32_t* __restrict__ idx2, float* __restrict__ dist2, uint8_t* __restrict__ accept)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    idx2[2 * i] = idx2[2 * i + 1] = -1;
+    dist2[2 * i] = dist2[2 * i + 1] = 3.402823466e+38f;
+    accept[i] = 0;
+}
+
+extern "C" int b200vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* t_dev, int nt, int dim, double ratio,
+                                     int32_t* idx2_dev, float* dist2_dev, uint8_t* accept_dev, int32_t* bad_dev)
+{
+    if (!ctx || !q_dev || !t_dev || !idx2_dev || !dist2_dev || !accept_dev) return B200VO_E_BADARG;
+    if (nq < 0 || nt < 0 || dim <= 0) return vo_set_err(ctx, B200VO_E_BADARG, "type == src2.type() && src1.cols == src2.cols");
+    if (dim != KNN_DIM) return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "descriptor length %d != 128 (SIFT)", dim);
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (bad_dev) VO_CUDA(ctx, cudaMemsetAsync(bad_dev, 0, 4, ctx->stream));
+    if (nq == 0) return 0;
+    if (nt == 0) {
+        knn_empty_train_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(nq, idx2_dev, dist2_dev, accept_dev);
+        ctx->launches++;
+        return 0;
+    }
+    VO_TRY(vo_knn2_ratio_dev(ctx, q_dev, nq, t_dev, nt, ratio, idx2_dev, dist2_dev, accept_dev, nullptr));
+    if (bad_dev) {
+        // the flag vo_knn2_ratio_dev keeps at the end of its scratch block (see its carve-up)
+        knn_export_flag_kernel<<<1, 1, 0, ctx->stream>>>(ctx->knn_bad_flag, bad_dev);
+        ctx->launches++;
+    }
     return 0;
 }
 
