@@ -389,13 +389,36 @@ class Arm:
             sb.step(None, h_lm_pts[f], h_lm_obj[f], h_n_lm[f], h_cand[f], h_n_cand[f])
         return dt, wall, devms
 
+    def h2d_bandwidth(self, nbytes=64 << 20):
+        """Page-locked host -> device copy bandwidth of this rank's link (GB/s, best of 5, CUDA events): the ceiling of
+        the end-to-end form, whose every step uploads one frame set."""
+        torch = self.torch
+        h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        best = 0.0
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            d.copy_(h, non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        return best
+
     def e2e(self):
         K = self.K
         sync_s, sync_wall, _ = self.timed_host_loop(False)
         s, wall, devms = self.timed_host_loop(True)
+        s_local = s
         s, sync_s = self.max_over_ranks([s, sync_s])
         h2d, d2h = self.wl.bytes_per_step()
-        return {"value": self.total * K / s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        link = guarded(self.h2d_bandwidth)
+        pcie = None
+        if isinstance(link, float) and link > 0:
+            pcie = {"h2d_gbs_measured": link, "h2d_gbs_achieved": h2d / (s_local / K) / 1e9, "frac": h2d / (s_local / K) / 1e9 / link,
+                    "note": "rank 0's link: bytes uploaded per step / end-to-end step time, against a plain 64 MiB page-locked copy; "
+                            "near 1 means the end-to-end form is bound by the host link, not by the kernels"}
+        return {"value": self.total * K / s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_link": pcie,
                 "ms_per_step": 1e3 * s / K, "host_ms_per_step": spread(wall), "device_ms_per_step": spread(devms),
                 "api": "b200vo_batch_submit_frames(t+1) + b200vo_batch_step(t): page-locked host buffers in and out, "
                        "next frames uploaded while the current step runs; per-step spread = wall clock around each call on rank 0, "

@@ -139,6 +139,12 @@ int b200vo_solve_pnp_ransac_p3p_dev(b200vo_ctx* ctx, const float* obj_dev, const
                                     double* pose_dev, int32_t* inliers_dev, int32_t* n_inliers_dev,
                                     uint8_t* success_dev);
 
+/* Measurement aid: b200vo_solve_pnp_ransac_p3p_dev with the fused pose kernel's phase stamps (SM clock of thread 0
+ * at its phase boundaries, see pnp.cu) returned in clk_host[16]; kernel_ms = CUDA-event time of the launch. */
+int b200vo_debug_pose_phases(b200vo_ctx* ctx, const float* obj_dev, const float* img_dev, int n,
+                             const double K[9], int iters, float reproj_err, double conf,
+                             long long* clk_host, float* kernel_ms);
+
 /*
  * ---- components next to the hot path ----
  *

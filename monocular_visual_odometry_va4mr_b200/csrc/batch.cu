@@ -11,6 +11,8 @@
 // Streams are a scarce resource: the driver multiplexes them onto 8 hardware queues by default
 // (CUDA_DEVICE_MAX_CONNECTIONS) and two streams on one queue serialise.  Chunks share 4 streams.
 #define B200VO_BATCH_STREAMS 4
+// host-buffer steps whose point arrays and results together stay below this go up / come back as ONE copy each
+#define B200VO_PACKED_IO_BYTES (512 * 1024)
 
 struct b200vo_batch {
     b200vo_ctx* ctx;
@@ -557,6 +559,23 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
         return cudaMemcpyAsync(di + off, hp + off, bytes, cudaMemcpyHostToDevice, st);
     };
     cudaStream_t ms = ctx->stream;
+    // Small batches (a single sequence, small shards): the step is latency-bound and a dozen separate DMA operations
+    // cost more than the kernels between them.  Pack: one host memcpy per array into the staging block, ONE upload;
+    // ONE read-back of the packed result block, host memcpy out.  Large batches keep the in-place DMA of every array.
+    const bool packed = in_bytes + out_bytes <= (size_t)B200VO_PACKED_IO_BYTES;
+    if (packed) {
+        memcpy(hp + o_lmp, lm_pts, (size_t)nb * L * 8);
+        memcpy(hp + o_lmo, lm_obj, (size_t)nb * L * 12);
+        memcpy(hp + o_nlm, n_lm, (size_t)nb * 4);
+        if (Cn > 0 && cand_pts && n_cand) {
+            memcpy(hp + o_cp, cand_pts, (size_t)nb * Cn * 8);
+            memcpy(hp + o_nc, n_cand, (size_t)nb * 4);
+        } else {
+            memset(hp + o_nc, 0, (size_t)nb * 4);
+        }
+        VO_CUDA(ctx, cudaMemcpyAsync(di, hp, in_bytes, cudaMemcpyHostToDevice, ms));
+        VO_CUDA(ctx, cudaEventRecord(B->done_ev, ctx->stream));
+    } else {
     VO_CUDA(ctx, upload(o_lmp, lm_pts, (size_t)nb * L * 8, ms));
     VO_CUDA(ctx, upload(o_nlm, n_lm, (size_t)nb * 4, ms));
     if (Cn > 0 && cand_pts && n_cand) {
@@ -570,6 +589,7 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->done_ev, 0));
     VO_CUDA(ctx, upload(o_lmo, lm_obj, (size_t)nb * L * 12, B->io_stream));
     VO_CUDA(ctx, cudaEventRecord(B->obj_ev, B->io_stream));
+    }
     if (prefetched) {
         VO_TRY(batch_issue_prefetch(B, B->done_ev));             // frames of later steps: behind this step's uploads
         VO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B->q_ev[q_slot], 0));
@@ -581,7 +601,7 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
         VO_TRY(batch_track_pose_overlapped(B, nullptr, (const float*)(di + o_lmp), (const float*)(di + o_lmo), (const int*)(di + o_nlm),
                                            (const float*)(di + o_cp), (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms,
                                            (float*)(dq + q_cn), dq + q_cs, (double*)(dq + q_pose), dq + q_ok, dq + q_mask,
-                                           (int*)(dq + q_ni), B->obj_ev));
+                                           (int*)(dq + q_ni), packed ? nullptr : B->obj_ev));
     } else {
         // The frames go up chunk by chunk, back to back on the copy stream; chunk k's pyramids + landmark tracker
         // run on a compute stream as soon as its frames have landed (the later chunks are on the wire meanwhile);
@@ -629,7 +649,7 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
         }
         VO_CUDA(ctx, cudaEventRecord(B->cand_ev, main_stream));
         // the pose chain (high priority) starts once every chunk's landmark tracks are done
-        VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->obj_ev, 0));
+        if (!packed) VO_CUDA(ctx, cudaStreamWaitEvent(B->pose_stream, B->obj_ev, 0));
         VO_CUDA(ctx, cudaEventRecord(B->lm_ev, B->pose_stream));
         ctx->stream = B->pose_stream;
         const int rc_pose = batch_pose(B, (const float*)(di + o_lmo), (const int*)(di + o_nlm), (const float*)(dq + q_lmn), dq + q_lms,
@@ -647,6 +667,15 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
                        {Cn > 0 ? cand_status : nullptr, q_cs, (size_t)nb * Cn, false},
                        {pose, q_pose, (size_t)nb * 48, false}, {pnp_ok, q_ok, (size_t)nb, false},
                        {inlier_mask, q_mask, (size_t)nb * L, false}, {n_inliers, q_ni, (size_t)nb * 4, false}};
+    if (packed) {
+        VO_CUDA(ctx, cudaMemcpyAsync(ho, dq, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+        for (auto& o : outs)
+            if (o.dst && o.bytes) memcpy(o.dst, ho + o.off, o.bytes);
+        return 0;
+    }
     // the tracker's results go home on the io stream while PnP runs; the pose results follow PnP
     VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->lm_ev, 0));
     for (int i = 0; i < 8; ++i) {

@@ -138,3 +138,36 @@ extern "C" int b200vo_solve_pnp_ransac_p3p_dev(b200vo_ctx* ctx, const float* obj
     VO_CUDA(ctx, cudaGetLastError());
     return 0;
 }
+
+// Measurement aid (benchmarks/pose_phases.py): the device-pointer PnP call with the fused kernel's phase stamps
+// (clock64 of thread 0 at the phase boundaries listed in pnp.cu) copied to clk_host[16] after a synchronisation.
+extern "C" int b200vo_debug_pose_phases(b200vo_ctx* ctx, const float* obj_dev, const float* img_dev, int n, const double K[9], int iters,
+                                        float reproj_err, double conf, long long* clk_host, float* kernel_ms)
+{
+    if (!ctx || !obj_dev || !img_dev || !K || !clk_host || n < 4) return B200VO_E_BADARG;
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PnpArgs a{};
+    a.batch = 1; a.cap = n; a.iters = iters < 1 ? 1 : iters;
+    a.fx = K[0]; a.fy = K[4]; a.cx = K[2]; a.cy = K[5];
+    a.thr_sq = (float)((double)reproj_err * (double)reproj_err);
+    a.conf = conf;
+    a.n_raw = 8 * a.iters + 256;
+    VO_TRY(vo_rng_table(ctx, a.n_raw, &a.rng_raw));
+    const size_t b_mask = vo_align((size_t)n, 256), b_inl = vo_align((size_t)n * 4, 256), b_ws = vo_pnp_workspace_bytes(1, n, a.iters);
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[1], 1024 + b_mask + b_inl + b_ws));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[1].p;
+    a.obj = obj_dev; a.img = img_dev; a.n = (const int*)d;
+    a.pose = (double*)(d + 64); a.ok = d + 128; a.phase_clk = (long long*)(d + 256);
+    a.mask = d + 1024; a.inliers = (int*)(d + 1024 + b_mask);
+    vo_pnp_carve_workspace(a, d + 1024 + b_mask + b_inl);
+    VO_CUDA(ctx, cudaMemsetAsync(d, 0, 1024, ctx->stream));
+    VO_CUDA(ctx, cudaMemcpyAsync(d, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (!vo_pnp_fused_ok(a, true)) return vo_set_err(ctx, B200VO_E_UNSUPPORTED, "the fused pose kernel is not in use for this size");
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    VO_TRY(vo_pnp_launch(ctx, a, true));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VO_CUDA(ctx, cudaMemcpyAsync(clk_host, a.phase_clk, 16 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (kernel_ms) cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1);
+    return 0;
+}

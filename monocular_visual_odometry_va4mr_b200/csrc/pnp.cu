@@ -246,6 +246,12 @@ pnp_select_kernel(PnpArgs a)
 // ------------------------------------------------------------------------------------------
 // 5. EPnP refit on the inliers (OpenCV epnp.cpp algorithm, float64 inputs)
 // ------------------------------------------------------------------------------------------
+// optional phase stamps (clock64 of thread 0) for benchmarks/pose_phases.py: PnpArgs::phase_clk, [batch][16]
+__device__ __forceinline__ void phase_stamp(const PnpArgs& a, int b, int k)
+{
+    if (a.phase_clk && threadIdx.x == 0) a.phase_clk[(size_t)b * 16 + k] = clock64();
+}
+
 #define EPNP_T 256
 #define EPNP_JT 160   // threads of the block that take part in the 12x12 eigen-decomposition (144 elements, 5 warps)
 
@@ -444,7 +450,7 @@ __device__ inline void epnp_gauss_newton(const double* L, const double* rho, dou
 // The refit, executed by one CTA of EPNP_T threads (every thread must call it; S is the CTA's scratch):
 // obj/img are this sequence's correspondences, inl[0..M) the inlier indices, pose_out receives rvec|tvec
 // (left untouched when the result is not finite -- the caller has put the RANSAC model there).
-__device__ inline void epnp_block(const PnpArgs& a, EpnpShared& S, const float* obj, const float* img, const int* inl, int M, double* pose_out)
+__device__ inline void epnp_block(const PnpArgs& a, EpnpShared& S, const float* obj, const float* img, const int* inl, int M, double* pose_out, int b)
 {
     const int tid = threadIdx.x;
     const double n = (double)M;
@@ -488,6 +494,7 @@ __device__ inline void epnp_block(const PnpArgs& a, EpnpShared& S, const float* 
         if (!inv3(cc, S.ci)) for (int k = 0; k < 9; ++k) S.ci[k] = nan("");
     }
     __syncthreads();
+    phase_stamp(a, b, 4);   // centroid, covariance, 3x3 SVD + control points done
     // pass 3: barycentric coordinates; M^T M in its 4x4-blocks-of-3x3 structure (40 sums) and the moments (16 sums).
     // The 56 sums are split over the two halves of the CTA (28 accumulators per thread instead of 56: the kernel has
     // to fit two CTAs per SM beside the tracker): threads 0-127 take the block pairs (0,0) (0,1) (0,2) (0,3) (1,1) and
@@ -563,6 +570,7 @@ __device__ inline void epnp_block(const PnpArgs& a, EpnpShared& S, const float* 
     if (tid >= 172 && tid < 176) S.mom_a[tid - 172] = S.out[52 + tid - 172];
     __syncthreads();
     const double Xbar[3] = {c0[0], c0[1], c0[2]};
+    phase_stamp(a, b, 5);   // M^T M assembled
     if (tid < EPNP_JT) {
         const int cur = block_jacobi_eig12(S, tid);
         const double* A = S.jac[cur];
@@ -579,6 +587,7 @@ __device__ inline void epnp_block(const PnpArgs& a, EpnpShared& S, const float* 
         }
     }
     __syncthreads();
+    phase_stamp(a, b, 6);   // 12x12 eigen-decomposition done
     if (tid < 6) {
         const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
         const int i = tid;
@@ -627,6 +636,7 @@ __device__ inline void epnp_block(const PnpArgs& a, EpnpShared& S, const float* 
         epnp_pose_from_betas(S, be, n, Xbar, S.Rs[Nn - 1], S.ts[Nn - 1]);
     }
     __syncthreads();
+    phase_stamp(a, b, 7);   // betas, Gauss-Newton, three candidate poses done
     // pass 4: mean reprojection error of the three candidates
     acc[0] = acc[1] = acc[2] = 0;
     for (int k = tid; k < M; k += EPNP_T) {
@@ -677,7 +687,7 @@ pnp_epnp_kernel(PnpArgs a)
     const int M = a.n_inliers[b];
     if (N == 4 || M < 4) return;   // N == 4: cv2 returns the direct P3P solve
     epnp_block(a, S, a.obj + (size_t)b * a.cap * 3, a.img + (size_t)b * a.cap * 2, a.inliers + (size_t)b * a.cap, M,
-               a.pose + (size_t)b * 6);
+               a.pose + (size_t)b * 6, b);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -777,6 +787,7 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
     int* inl = a.inliers + (size_t)b * a.cap;
     int* orig = io.c_orig ? io.c_orig + (size_t)b * a.cap : nullptr;
 
+    phase_stamp(a, b, 0);
     // ---- 1. status == 1 landmarks, in order (what `matched_pts[tracked]` does in the reference, :282-284) ----
     if (tid == 0) F.base = 0;
     __syncthreads();
@@ -814,6 +825,7 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
     }
     __syncthreads();
 
+    phase_stamp(a, b, 1);   // compaction done
     // ---- 2. RANSAC in chunks of 32 hypotheses; thread 0 replays cv2's loop after each chunk ----
     while (F.it0 < F.niters) {                       // block-uniform: both change only between barriers
         const int it0 = F.it0;
@@ -824,6 +836,7 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
         }
         if (tid < FUSED_CHUNK) F.cnt[tid] = 0;
         __syncthreads();
+        phase_stamp(a, b, 9);    // (last chunk) subsets drawn
         // one hypothesis per thread, spread over the warps (P3P branches diverge: 4 per warp, 8 warps issue in parallel)
         if ((tid & 7) == 0) {
             const int h = tid >> 3;
@@ -832,6 +845,7 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
             F.ok[h] = okh;
         }
         __syncthreads();
+        phase_stamp(a, b, 10);   // (last chunk) minimal solves done
         if (N > 4) {
             for (int base = 0; base < N; base += FUSED_T) {
                 const int i = base + tid;
@@ -848,6 +862,7 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
             }
             __syncthreads();
         }
+        phase_stamp(a, b, 11);   // (last chunk) scoring done
         if (tid == 0) {
             int niters = F.niters, max_good = F.max_good, win = F.win;
             if (N == 4) { win = F.ok[0] ? 0 : -1; if (win == 0) { for (int k = 0; k < 12; ++k) F.win_h[k] = F.h[k]; for (int k = 0; k < 3; ++k) F.win_rv[k] = F.rv[k]; } }
@@ -868,6 +883,7 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
         __syncthreads();
     }
 
+    phase_stamp(a, b, 2);   // RANSAC chunks done
     // ---- 3. winner mask + ordered inlier list ----
     const int win = F.win;
     int M = 0;
@@ -905,9 +921,11 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
             pose[3] = F.win_h[9]; pose[4] = F.win_h[10]; pose[5] = F.win_h[11];
         }
         __syncthreads();
+        phase_stamp(a, b, 3);   // winner mask + inlier list done
         // ---- 4. EPnP refit on the inliers (N == 4: cv2 returns the direct P3P solve) ----
-        if (N != 4 && M >= 4) epnp_block(a, S, obj, img, inl, M, pose);
+        if (N != 4 && M >= 4) epnp_block(a, S, obj, img, inl, M, pose, b);
     }
+    phase_stamp(a, b, 8);   // EPnP done
     // ---- 5. inlier mask over the ORIGINAL landmark slots (:346) ----
     if (io.mask_out) {
         __syncthreads();

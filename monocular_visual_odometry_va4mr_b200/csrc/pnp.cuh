@@ -31,6 +31,7 @@ struct PnpArgs {
     int full_counts;        // 1: score every hypothesis (the caller reads counts[]); no early exit
     int head;               // 1: this is the head chunk (computes need[]); 0: tail chunk (honours need[])
     uint8_t* ok_ws;         // [batch] spare per-sequence success flags (callers may point `ok` here)
+    long long* phase_clk;   // optional [batch][16] clock64 stamps of the fused kernel's phases (benchmarks/pose_phases.py); usually null
     // outputs
     int* inliers;           // [batch][cap] ascending indices
     uint8_t* mask;          // [batch][cap]
