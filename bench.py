@@ -110,6 +110,22 @@ def summarize_clocks(samples):
             "reasons": sorted(reasons), "samples": len(samples)}
 
 
+def pin_to_gpu_cores(dev):
+    """Restrict this rank to the CPU cores NVML lists as local to its GPU (first-touch then places the rank's
+    page-locked buffers on that NUMA node).  -> number of cores, or None when NVML has no answer."""
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+    n_words = (os.cpu_count() + 63) // 64
+    mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+    cores = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+    cores = [c for c in cores if c in os.sched_getaffinity(0)]
+    if not cores:
+        return None
+    os.sched_setaffinity(0, cores)
+    return len(cores)
+
+
 def guarded(fn, *a, **kw):
     """Run a non-headline measurement; a failure becomes {"error": ...} on the JSON line."""
     try:
@@ -650,7 +666,9 @@ def main(argv=None):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the cv2 path)")
     torch.cuda.set_device(local)
+    affinity = None
     if world > 1:
+        affinity = guarded(pin_to_gpu_cores, local)     # each rank on the cores (NUMA node) next to its GPU: its page-locked pool lands there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from monocular_visual_odometry_va4mr_b200 import _lib, sharding
     ctx = _lib.Context(local)
@@ -715,6 +733,7 @@ def main(argv=None):
                                         "b200vo_batch_step_dev(frames=NULL)" if not args.no_lookahead else "b200vo_batch_step_dev(frames)"),
                            parallelism=f"sequences sharded x{world} ({args.scaling} scaling), NCCL all_gather of poses"),
             "clocks": clocks,
+            "cpu_affinity_cores": affinity,
             "e2e": e2e,
             "gpu_launches": res["launches"],
             "roofline": roofline,

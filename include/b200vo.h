@@ -145,6 +145,13 @@ int b200vo_debug_pose_phases(b200vo_ctx* ctx, const float* obj_dev, const float*
                              const double K[9], int iters, float reproj_err, double conf,
                              long long* clk_host, float* kernel_ms);
 
+/* Self-check of the float32 pre-test inside the fused pose kernel's scoring loop: random poses / landmarks with image
+ * points whose squared residual sits at threshold * (1 +- 1e-7 .. 1e-1); tally = {trials, decided by the pre-test,
+ * decided differently from the exact FP64 decision} -- the last must be 0. */
+int b200vo_debug_pnp_pretest_check(b200vo_ctx* ctx, unsigned long long seed, int blocks, int per_thread,
+                                   const double K[9], float reproj_err, double depth_lo, double depth_hi,
+                                   unsigned long long tally[3]);
+
 /*
  * ---- components next to the hot path ----
  *
@@ -173,6 +180,25 @@ int b200vo_triangulate_landmarks(b200vo_ctx* ctx, const double K[9], double min_
                                  int n, const double* poses_cw, int n_poses,
                                  const double cur_pose_cw[12], uint8_t* too_short_baseline,
                                  float* new_landmarks, float* new_keypoints, int* n_new);
+/*
+ * Batched forms of the two components above ("batched f1/f2 on the resident batch state"): the same
+ * per-sequence work for every sequence of a batch, one or two launches for the whole batch.  Arrays carry a leading
+ * batch axis and a fixed capacity per sequence; n / m / n_poses give the live rows of each sequence.
+ *   pts (batch,n_cap,2), existing (batch,m_cap,2) float32 -> valid uint8 (batch,n_cap) (rows >= n[s] are 0).
+ *   first_keys / keys (batch,cap,2) float32, first_pose (batch,cap) int32, poses_cw (batch,pose_cap,12) double,
+ *   cur_pose_cw (batch,12) double -> too_short_baseline uint8 (batch,cap), new_landmarks (batch,cap,3) and
+ *   new_keypoints (batch,cap,2) float32 compacted per sequence, n_new int32 (batch).
+ */
+int b200vo_batch_min_distance_mask(b200vo_ctx* ctx, int batch, const float* pts, const int32_t* n, int n_cap,
+                                   const float* existing, const int32_t* m, int m_cap, float min_dist,
+                                   uint8_t* valid);
+int b200vo_batch_triangulate_landmarks(b200vo_ctx* ctx, const double K[9], double min_dist, double max_dist,
+                                       double min_baseline_angle_deg, int min_baseline_frames, int batch,
+                                       int cap, const float* first_keys, const float* keys,
+                                       const int32_t* first_pose, const int32_t* n, const double* poses_cw,
+                                       const int32_t* n_poses, int pose_cap, const double* cur_pose_cw,
+                                       uint8_t* too_short_baseline, float* new_landmarks,
+                                       float* new_keypoints, int32_t* n_new);
 
 /*
  * Replaces cv2.recoverPose(E, points1, points2, K) at :315 (default distanceThresh = 50):

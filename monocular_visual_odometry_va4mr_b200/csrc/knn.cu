@@ -517,9 +517,11 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
 {
     const int nq_pad = (int)vo_align((size_t)nq, KNN_BM), nt_pad = (int)vo_align((size_t)nt, KNN_BN);
     const int m_tiles = nq_pad / KNN_BM, n_tiles = nt_pad / KNN_BN;
-    // flat schedule (default): one contiguous run of (query tile, train tile) pairs per SM; B200VO_KNN=v1 keeps the
-    // first kernel (m_tiles x floor(SMs / m_tiles) CTAs) for A/B runs
-    static const bool use_v1 = getenv("B200VO_KNN") && !strcmp(getenv("B200VO_KNN"), "v1");
+    // B200VO_KNN=flat selects the flat schedule (one contiguous run of (query tile, train tile) pairs per SM, all 148
+    // SMs busy); measured at 8192 x 8192 (profiles/r2d_knn_*): 39.1 us against 34.4 us for the first kernel
+    // (m_tiles x floor(SMs / m_tiles) = 128 CTAs) -- its 16-column epilogue pieces expose the TMEM load latency four
+    // times per tile instead of twice -- so the first kernel stays the default until the flat one wins
+    static const bool use_v1 = !(getenv("B200VO_KNN") && !strcmp(getenv("B200VO_KNN"), "flat"));
     const int total = m_tiles * n_tiles;
     const int per = (total + ctx->num_sms - 1) / ctx->num_sms;
     int n_splits;

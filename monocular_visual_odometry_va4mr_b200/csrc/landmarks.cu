@@ -69,11 +69,8 @@ __device__ __forceinline__ void proj_matrix(const double* K, const double* R, co
 }
 
 // ---- f1: one thread per candidate ----
-__global__ void __launch_bounds__(64)
-triangulate_kernel(TriArgs a)
+__device__ __forceinline__ void triangulate_one(const TriArgs& a, int i)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
     a.keep[i] = 1;
     const int fp = a.first_pose[i];
     if (a.n_poses > 1 && a.n_poses - fp <= a.min_frames) return;
@@ -123,9 +120,15 @@ triangulate_kernel(TriArgs a)
     }
 }
 
+__global__ void __launch_bounds__(64)
+triangulate_kernel(TriArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) triangulate_one(a, i);
+}
+
 // ordered compaction of the accepted candidates (keep == 0): one CTA, ballot + running base
-__global__ void __launch_bounds__(1024)
-triangulate_compact_kernel(TriArgs a)
+__device__ __forceinline__ void triangulate_compact_block(const TriArgs& a)
 {
     __shared__ int s_warp[32];
     __shared__ int s_base;
@@ -154,6 +157,76 @@ triangulate_compact_kernel(TriArgs a)
         __syncthreads();
     }
     if (threadIdx.x == 0) *a.n_new = s_base;
+}
+
+__global__ void __launch_bounds__(1024)
+triangulate_compact_kernel(TriArgs a) { triangulate_compact_block(a); }
+
+// ---- batched forms (SURVEY 8f "batched f1/f2 on the resident batch state"): the same per-sequence work for every
+// sequence of a batch in one launch each; blockIdx.y = sequence, ragged counts per sequence ----
+struct TriBatchArgs {
+    TriArgs common;            // K, Ki, gates (the per-sequence fields are filled in by the kernels)
+    int cap, pose_cap;
+    const int* n;              // [batch] candidates per sequence
+    const int* n_poses;        // [batch]
+    const double* cur;         // [batch][12]
+    const float* first_keys; const float* keys; const int* first_pose;   // [batch][cap]...
+    const double* poses;       // [batch][pose_cap][12]
+    uint8_t* keep; float* lm_slot; float* out_lm; float* out_kp; int* n_new; int* flags;   // [batch]...
+};
+
+__device__ __forceinline__ TriArgs tri_sequence(const TriBatchArgs& b, int s)
+{
+    TriArgs a = b.common;
+    const size_t o = (size_t)s * b.cap;
+    a.n = min(max(b.n[s], 0), b.cap);
+    a.n_poses = min(max(b.n_poses[s], 0), b.pose_cap);
+    for (int k = 0; k < 12; ++k) a.cur[k] = b.cur[12 * s + k];
+    a.first_keys = b.first_keys + 2 * o; a.keys = b.keys + 2 * o; a.first_pose = b.first_pose + o;
+    a.poses = b.poses + (size_t)s * b.pose_cap * 12;
+    a.keep = b.keep + o; a.lm_slot = b.lm_slot + 3 * o; a.out_lm = b.out_lm + 3 * o; a.out_kp = b.out_kp + 2 * o;
+    a.n_new = b.n_new + s; a.flags = b.flags + s;
+    return a;
+}
+
+__global__ void __launch_bounds__(64)
+triangulate_batch_kernel(TriBatchArgs b)
+{
+    const TriArgs a = tri_sequence(b, blockIdx.y);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.n_poses < 1) { if (i < a.n) a.keep[i] = 1; return; }
+    if (i < a.n) triangulate_one(a, i);
+}
+
+__global__ void __launch_bounds__(1024)
+triangulate_compact_batch_kernel(TriBatchArgs b)
+{
+    const TriArgs a = tri_sequence(b, blockIdx.x);
+    triangulate_compact_block(a);
+}
+
+__global__ void __launch_bounds__(256)
+min_distance_batch_kernel(const float2* __restrict__ pts, const int* __restrict__ n, int n_cap, const float2* __restrict__ existing,
+                          const int* __restrict__ m, int m_cap, float min_dist, uint8_t* __restrict__ valid)
+{
+    const int s = blockIdx.y;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= min(max(n[s], 0), n_cap)) return;
+    const float2 p = pts[(size_t)s * n_cap + i];
+    const float2* ex = existing + (size_t)s * m_cap;
+    const int ms = min(max(m[s], 0), m_cap);
+    bool ok = true;
+    for (int j0 = 0; j0 < ms; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < ms) {
+            const float2 q = ex[j];
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y);
+            const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+            ok = d > min_dist;           // NaN compares false, as in numpy
+        }
+        if (!__all_sync(0xffffffffu, ok)) { ok = false; break; }
+    }
+    if (lane == 0) valid[(size_t)s * n_cap + i] = ok ? 1 : 0;
 }
 
 extern "C" int b200vo_min_distance_mask(b200vo_ctx* ctx, const float* pts, int n, const float* existing, int m,
@@ -240,6 +313,106 @@ extern "C" int b200vo_triangulate_landmarks(b200vo_ctx* ctx, const double K[9], 
     memcpy(new_landmarks, ho + b_keep, (size_t)cnt * 12);
     memcpy(new_keypoints, ho + b_keep + b_lm, (size_t)cnt * 8);
     *n_new = cnt;
+    return 0;
+}
+
+// Batched f2: the candidate min-distance filter (:258) for every sequence of a batch in one launch.
+// pts float32 (batch, n_cap, 2) with n[batch] live rows, existing float32 (batch, m_cap, 2) with m[batch]; valid uint8 (batch, n_cap).
+extern "C" int b200vo_batch_min_distance_mask(b200vo_ctx* ctx, int batch, const float* pts, const int32_t* n, int n_cap,
+                                              const float* existing, const int32_t* m, int m_cap, float min_dist, uint8_t* valid)
+{
+    if (!ctx || batch < 1 || n_cap < 1 || m_cap < 0 || !pts || !n || !m || !valid || (m_cap > 0 && !existing)) return B200VO_E_BADARG;
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const int mc = m_cap > 0 ? m_cap : 1;
+    const size_t b_p = vo_align((size_t)batch * n_cap * 8, 256), b_e = vo_align((size_t)batch * mc * 8, 256);
+    const size_t b_c = vo_align((size_t)batch * 4, 256), b_v = vo_align((size_t)batch * n_cap, 256);
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[6], b_p + b_e + 2 * b_c + b_v));
+    VO_TRY(vo_reserve_pinned(ctx, b_p + b_e + 2 * b_c + b_v));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[6].p;
+    uint8_t* hp = (uint8_t*)ctx->h_pin;
+    memcpy(hp, pts, (size_t)batch * n_cap * 8);
+    if (m_cap > 0) memcpy(hp + b_p, existing, (size_t)batch * m_cap * 8);
+    memcpy(hp + b_p + b_e, n, (size_t)batch * 4);
+    memcpy(hp + b_p + b_e + b_c, m, (size_t)batch * 4);
+    VO_CUDA(ctx, cudaMemcpyAsync(d, hp, b_p + b_e + 2 * b_c, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* dv = d + b_p + b_e + 2 * b_c;
+    VO_CUDA(ctx, cudaMemsetAsync(dv, 0, b_v, ctx->stream));
+    min_distance_batch_kernel<<<dim3((n_cap * 32 + 255) / 256, batch), 256, 0, ctx->stream>>>(
+        (const float2*)d, (const int*)(d + b_p + b_e), n_cap, (const float2*)(d + b_p), (const int*)(d + b_p + b_e + b_c), m_cap, min_dist, dv);
+    ctx->launches++;
+    VO_CUDA(ctx, cudaGetLastError());
+    uint8_t* ho = hp + b_p + b_e + 2 * b_c;
+    VO_CUDA(ctx, cudaMemcpyAsync(ho, dv, (size_t)batch * n_cap, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    memcpy(valid, ho, (size_t)batch * n_cap);
+    return 0;
+}
+
+// Batched f1: the candidate loop of triangulate_landmarks (:170-204) for every sequence of a batch: two launches.
+// Per sequence s: n[s] candidates in rows [0, n[s]) of the (batch, cap, ...) arrays, n_poses[s] stored poses in
+// poses_cw (batch, pose_cap, 12), the current pose cur_pose_cw (batch, 12).  Outputs: too_short_baseline uint8 (batch, cap),
+// new_landmarks float32 (batch, cap, 3) / new_keypoints float32 (batch, cap, 2) compacted per sequence, n_new int32 (batch).
+extern "C" int b200vo_batch_triangulate_landmarks(b200vo_ctx* ctx, const double K[9], double min_dist, double max_dist,
+                                                  double min_baseline_angle_deg, int min_baseline_frames, int batch, int cap,
+                                                  const float* first_keys, const float* keys, const int32_t* first_pose,
+                                                  const int32_t* n, const double* poses_cw, const int32_t* n_poses, int pose_cap,
+                                                  const double* cur_pose_cw, uint8_t* too_short_baseline, float* new_landmarks,
+                                                  float* new_keypoints, int32_t* n_new)
+{
+    if (!ctx || !K || batch < 1 || cap < 1 || pose_cap < 1 || !first_keys || !keys || !first_pose || !n || !poses_cw || !n_poses ||
+        !cur_pose_cw || !too_short_baseline || !new_landmarks || !new_keypoints || !n_new)
+        return B200VO_E_BADARG;
+    VO_CUDA(ctx, cudaSetDevice(ctx->device));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    TriBatchArgs b{};
+    for (int k = 0; k < 9; ++k) b.common.K[k] = K[k];
+    const double Ki[9] = {1.0 / K[0], 0, -K[2] / K[0], 0, 1.0 / K[4], -K[5] / K[4], 0, 0, 1};
+    for (int k = 0; k < 9; ++k) b.common.Ki[k] = Ki[k];
+    b.common.min_dist = min_dist; b.common.max_dist = max_dist; b.common.min_angle_deg = min_baseline_angle_deg;
+    b.common.min_frames = min_baseline_frames;
+    b.cap = cap; b.pose_cap = pose_cap;
+    const size_t nc = (size_t)batch * cap;
+    const size_t b_k = vo_align(nc * 8, 256), b_fp = vo_align(nc * 4, 256), b_ps = vo_align((size_t)batch * pose_cap * 96, 256);
+    const size_t b_cnt = vo_align((size_t)batch * 4, 256), b_cur = vo_align((size_t)batch * 96, 256);
+    const size_t b_keep = vo_align(nc, 256), b_lm = vo_align(nc * 12, 256);
+    const size_t in_bytes = 2 * b_k + b_fp + b_ps + 2 * b_cnt + b_cur, out_bytes = b_keep + b_lm + b_k + 2 * b_cnt;
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[7], in_bytes + out_bytes + b_lm));
+    VO_TRY(vo_reserve_pinned(ctx, in_bytes + out_bytes));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[7].p;
+    uint8_t* hp = (uint8_t*)ctx->h_pin;
+    size_t o = 0;
+    memcpy(hp + o, first_keys, nc * 8); b.first_keys = (const float*)(d + o); o += b_k;
+    memcpy(hp + o, keys, nc * 8); b.keys = (const float*)(d + o); o += b_k;
+    memcpy(hp + o, first_pose, nc * 4); b.first_pose = (const int*)(d + o); o += b_fp;
+    memcpy(hp + o, poses_cw, (size_t)batch * pose_cap * 96); b.poses = (const double*)(d + o); o += b_ps;
+    memcpy(hp + o, n, (size_t)batch * 4); b.n = (const int*)(d + o); o += b_cnt;
+    memcpy(hp + o, n_poses, (size_t)batch * 4); b.n_poses = (const int*)(d + o); o += b_cnt;
+    memcpy(hp + o, cur_pose_cw, (size_t)batch * 96); b.cur = (const double*)(d + o); o += b_cur;
+    VO_CUDA(ctx, cudaMemcpyAsync(d, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* dout = d + in_bytes;
+    b.keep = dout; b.out_lm = (float*)(dout + b_keep); b.out_kp = (float*)(dout + b_keep + b_lm);
+    b.n_new = (int*)(dout + b_keep + b_lm + b_k); b.flags = (int*)(dout + b_keep + b_lm + b_k + b_cnt);
+    b.lm_slot = (float*)(dout + out_bytes);
+    VO_CUDA(ctx, cudaMemsetAsync(dout, 0, out_bytes, ctx->stream));
+    triangulate_batch_kernel<<<dim3((cap + 63) / 64, batch), 64, 0, ctx->stream>>>(b);
+    triangulate_compact_batch_kernel<<<batch, 1024, 0, ctx->stream>>>(b);
+    ctx->launches += 2;
+    VO_CUDA(ctx, cudaGetLastError());
+    uint8_t* ho = hp + in_bytes;
+    VO_CUDA(ctx, cudaMemcpyAsync(ho, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    const int* flg = (const int*)(ho + b_keep + b_lm + b_k + b_cnt);
+    for (int s = 0; s < batch; ++s)
+        if (flg[s] & 1) return vo_set_err(ctx, B200VO_E_BADARG, "sequence %d: first_pose index outside [0, n_poses)", s);
+    memcpy(too_short_baseline, ho, nc);
+    memcpy(new_landmarks, ho + b_keep, nc * 12);
+    memcpy(new_keypoints, ho + b_keep + b_lm, nc * 8);
+    memcpy(n_new, ho + b_keep + b_lm + b_k, (size_t)batch * 4);
     return 0;
 }
 

@@ -8,6 +8,31 @@
 
 namespace vo {
 
+// 1/sqrt(x) and 1/x to ~1 ulp without the library's IEEE routines (long dependent FP64 chains on this part): hardware
+// float seed (22 bits) + two Newton steps in double.  Outside the float range of the seed the exact forms are used.
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    if (!(x > 1e-30 && x < 1e30)) return 1.0 / sqrt(x);
+    float yf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)x));
+    double y = (double)yf;
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return y;
+}
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    const double ax = fabs(x);
+    if (!(ax > 1e-30 && ax < 1e30)) return 1.0 / x;
+    float yf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)x));
+    double y = (double)yf;
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
 __device__ __forceinline__ double det3(const double* M)
 {
     return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
@@ -194,8 +219,8 @@ __device__ inline void qr_lstsq6(const double* Ain, const double* bin, double* x
         double nrm = 0;
 #pragma unroll
         for (int i = k; i < M; ++i) nrm += A[i * NC + k] * A[i * NC + k];
-        nrm = sqrt(nrm);
         if (nrm == 0) continue;
+        nrm = nrm * rsqrt_fast(nrm);      // sqrt
         const double alpha = A[k * NC + k] > 0 ? -nrm : nrm;
         double v[M];
 #pragma unroll
@@ -205,7 +230,7 @@ __device__ inline void qr_lstsq6(const double* Ain, const double* bin, double* x
 #pragma unroll
         for (int i = k; i < M; ++i) vn += v[i] * v[i];
         if (vn == 0) continue;
-        const double tau = 2.0 / vn;      // H = I - tau v v^T: one division per reflector instead of one per column
+        const double tau = 2.0 * rcp_fast(vn);      // H = I - tau v v^T: one reciprocal per reflector instead of a division per column
 #pragma unroll
         for (int j = k; j < NC; ++j) {
             double s = 0;
@@ -227,7 +252,7 @@ __device__ inline void qr_lstsq6(const double* Ain, const double* bin, double* x
         double s = b[k];
 #pragma unroll
         for (int j = k + 1; j < NC; ++j) s -= A[k * NC + j] * x[j];
-        x[k] = A[k * NC + k] != 0 ? s / A[k * NC + k] : 0;
+        x[k] = A[k * NC + k] != 0 ? s * rcp_fast(A[k * NC + k]) : 0;
     }
 }
 

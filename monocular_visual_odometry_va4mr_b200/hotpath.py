@@ -100,3 +100,51 @@ def find_essential_mat_samples(p1, p2, K, samples, prob=0.999, threshold=1.0, wa
         _p(models, c_f64p) if want_models else None, C.byref(winner), C.byref(run)), "b200vo_find_essential_mat_ransac_samples")
     return dict(E=E.reshape(3, 3) if found.value else None, mask=mask if found.value else None, nmodels=nmodels, counts=counts,
                 models=models, winner=winner.value, iters_run=run.value)
+
+
+def batch_min_distance_mask(pts, n, potential_keys, m, min_dist, ctx: _lib.Context | None = None) -> np.ndarray:
+    """``min_distance_mask`` for every sequence of a batch in one launch: ``pts`` float32 (batch, n_cap, 2) with ``n``
+    (batch,) live rows, ``potential_keys`` float32 (batch, m_cap, 2) with ``m`` (batch,) live rows.
+    -> bool (batch, n_cap); rows beyond n[s] are False."""
+    ctx = ctx or _lib.default_context(0)
+    pts = np.ascontiguousarray(pts, np.float32)
+    ex = np.ascontiguousarray(potential_keys, np.float32)
+    batch, n_cap = pts.shape[0], pts.shape[1]
+    m_cap = ex.shape[1] if ex.ndim == 3 else 0
+    n = np.ascontiguousarray(n, np.int32).reshape(batch)
+    m = np.ascontiguousarray(m, np.int32).reshape(batch)
+    valid = np.zeros((batch, n_cap), np.uint8)
+    _chk(ctx, ctx.lib.b200vo_batch_min_distance_mask(ctx.h, batch, _p(pts, c_f32p), _p(n, c_i32p), n_cap,
+                                                     _p(ex, c_f32p) if m_cap else None, _p(m, c_i32p), m_cap, C.c_float(min_dist),
+                                                     _p(valid, c_u8p)), "b200vo_batch_min_distance_mask")
+    return valid.astype(bool)
+
+
+def batch_triangulate_landmarks(K, options, potential_first_keys, potential_keys, potential_transforms, n, poses, n_poses, cur_poses,
+                                ctx: _lib.Context | None = None):
+    """``triangulate_landmarks`` for every sequence of a batch (two launches).  Arrays carry a leading batch axis and a fixed
+    capacity: first_keys / keys float32 (batch, cap, 2), potential_transforms int (batch, cap), ``n`` (batch,) live candidates;
+    ``poses`` float64 (batch, pose_cap, 12) (see ``pack_poses``) with ``n_poses`` (batch,), ``cur_poses`` float64 (batch, 12).
+    -> (too_short_baseline bool (batch, cap), new_landmarks float32 (batch, cap, 3), new_keypoints float32 (batch, cap, 2),
+    n_new int32 (batch,)); the new rows of sequence s are [:n_new[s]]."""
+    ctx = ctx or _lib.default_context(0)
+    fk = np.ascontiguousarray(potential_first_keys, np.float32)
+    k = np.ascontiguousarray(potential_keys, np.float32)
+    batch, cap = k.shape[0], k.shape[1]
+    fp = np.ascontiguousarray(potential_transforms, np.int32).reshape(batch, cap)
+    n = np.ascontiguousarray(n, np.int32).reshape(batch)
+    poses = np.ascontiguousarray(poses, np.float64)
+    pose_cap = poses.shape[1]
+    n_poses = np.ascontiguousarray(n_poses, np.int32).reshape(batch)
+    cur = np.ascontiguousarray(cur_poses, np.float64).reshape(batch, 12)
+    Kf = np.ascontiguousarray(K, np.float64).reshape(9)
+    keep = np.zeros((batch, cap), np.uint8)
+    lm = np.zeros((batch, cap, 3), np.float32)
+    kp = np.zeros((batch, cap, 2), np.float32)
+    n_new = np.zeros(batch, np.int32)
+    _chk(ctx, ctx.lib.b200vo_batch_triangulate_landmarks(
+        ctx.h, _p(Kf, c_f64p), C.c_double(options['min_dist_landmarks']), C.c_double(options['max_dist_landmarks']),
+        C.c_double(options['min_baseline_angle']), int(options['min_baseline_frames']), batch, cap, _p(fk, c_f32p), _p(k, c_f32p),
+        _p(fp, c_i32p), _p(n, c_i32p), _p(poses, c_f64p), _p(n_poses, c_i32p), pose_cap, _p(cur, c_f64p), _p(keep, c_u8p),
+        _p(lm, c_f32p), _p(kp, c_f32p), _p(n_new, c_i32p)), "b200vo_batch_triangulate_landmarks")
+    return keep.astype(bool), lm, kp, n_new

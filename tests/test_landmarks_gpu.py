@@ -94,3 +94,44 @@ def test_recover_pose_vs_oracle_and_live_cv2(g):
         assert good == gc and np.array_equal(mask, mc) and np.abs(R - Rc).max() < 1e-12 and np.abs(t - tc).max() < 1e-12
     with pytest.raises(NotImplementedError):
         cv2_compat.recoverPose(E, p1, p2)
+
+
+def test_batched_forms_equal_the_per_sequence_calls(g):
+    """SURVEY 8f, "batched f1/f2": one or two launches for a whole batch of sequences, ragged counts, identical results
+    to calling the per-sequence entry for each sequence (which the tests above pin to the reference's own run)."""
+    rng = np.random.default_rng(11)
+    # ---- f2: ragged sets, planted exact ties ----
+    batch, n_cap, m_cap = 7, 96, 160
+    n = np.array([96, 0, 40, 1, 77, 96, 13], np.int32)
+    m = np.array([160, 50, 0, 1, 160, 31, 99], np.int32)
+    pts = np.rint(rng.uniform(0, 600, (batch, n_cap, 2))).astype(np.float32)
+    ex = rng.uniform(0, 600, (batch, m_cap, 2)).astype(np.float32)
+    ex[0, 0] = pts[0, 0] + np.float32([6, 8])                                                   # distance == 10: not > 10
+    ex[4, 1] = pts[4, 1] + np.float32([6, np.nextafter(np.float32(8), np.float32(9))])           # one step above
+    got = hotpath.batch_min_distance_mask(pts, n, ex, m, 10.0)
+    assert got.shape == (batch, n_cap) and got.dtype == bool
+    for s in range(batch):
+        want = hotpath.min_distance_mask(pts[s, :n[s]], ex[s, :m[s]], 10.0)
+        assert np.array_equal(got[s, :n[s]], want) and not got[s, n[s]:].any(), s
+    # ---- f1: the recorded reference calls as sequences of one batch (different candidate counts and pose histories) ----
+    nt = sum(1 for k in g.files if k.startswith("tri") and k.endswith("_keep"))
+    seqs = list(range(nt)) + [0]                                   # one sequence twice, truncated the second time
+    cap = max(len(g[f"tri{i}_keys"]) for i in range(nt)) + 5
+    pose_cap = max(len(g[f"tri{i}_poses"]) for i in range(nt)) + 2
+    B = len(seqs)
+    fk = np.zeros((B, cap, 2), np.float32); k = np.zeros((B, cap, 2), np.float32); fp = np.zeros((B, cap), np.int32)
+    nn = np.zeros(B, np.int32); poses = np.zeros((B, pose_cap, 12)); npz = np.zeros(B, np.int32); cur = np.zeros((B, 12))
+    for s, i in enumerate(seqs):
+        cnt = len(g[f"tri{i}_keys"]) if s < nt else 37
+        fk[s, :cnt] = g[f"tri{i}_first_keys"].reshape(-1, 2)[:cnt]; k[s, :cnt] = g[f"tri{i}_keys"].reshape(-1, 2)[:cnt]
+        fp[s, :cnt] = np.asarray(g[f"tri{i}_first_pose"]).reshape(-1)[:cnt]
+        nn[s] = cnt
+        P = np.asarray(g[f"tri{i}_poses"]).reshape(-1, 12)
+        poses[s, :len(P)] = P; npz[s] = len(P); cur[s] = g[f"tri{i}_cur"]
+    keep, lm, kp, n_new = hotpath.batch_triangulate_landmarks(g["K"], OPT(g["tri_cfg"]), fk, k, fp, nn, poses, npz, cur)
+    for s, i in enumerate(seqs):
+        cnt = int(nn[s])
+        wk, wl, wp = hotpath.triangulate_landmarks(g["K"], OPT(g["tri_cfg"]), fk[s, :cnt], k[s, :cnt], fp[s, :cnt], poses[s, :npz[s]],
+                                                   cur[s, :9].reshape(3, 3), cur[s, 9:])
+        assert np.array_equal(keep[s, :cnt], wk) and int(n_new[s]) == len(wl), s
+        assert np.array_equal(lm[s, :n_new[s]], wl) and np.array_equal(kp[s, :n_new[s]], wp), s
