@@ -145,13 +145,6 @@ int b200vo_debug_pose_phases(b200vo_ctx* ctx, const float* obj_dev, const float*
                              const double K[9], int iters, float reproj_err, double conf,
                              long long* clk_host, float* kernel_ms);
 
-/* Self-check of the float32 pre-test inside the fused pose kernel's scoring loop: random poses / landmarks with image
- * points whose squared residual sits at threshold * (1 +- 1e-7 .. 1e-1); tally = {trials, decided by the pre-test,
- * decided differently from the exact FP64 decision} -- the last must be 0. */
-int b200vo_debug_pnp_pretest_check(b200vo_ctx* ctx, unsigned long long seed, int blocks, int per_thread,
-                                   const double K[9], float reproj_err, double depth_lo, double depth_hi,
-                                   unsigned long long tally[3]);
-
 /*
  * ---- components next to the hot path ----
  *

@@ -172,23 +172,3 @@ extern "C" int b200vo_debug_pose_phases(b200vo_ctx* ctx, const float* obj_dev, c
     return 0;
 }
 
-// Self-check of the scoring pre-test (see pnp_pretest_check_kernel): tally[3] = trials, decided by the float pre-test,
-// decided differently from the exact FP64 form (must be 0).
-__global__ void pnp_pretest_check_kernel(unsigned long long seed, int per_thread, double fx, double fy, double cx, double cy, float thr_sq,
-                                         double depth_lo, double depth_hi, unsigned long long* tally);
-extern "C" int b200vo_debug_pnp_pretest_check(b200vo_ctx* ctx, unsigned long long seed, int blocks, int per_thread, const double K[9],
-                                              float reproj_err, double depth_lo, double depth_hi, unsigned long long tally[3])
-{
-    if (!ctx || !K || !tally || blocks < 1 || per_thread < 1) return B200VO_E_BADARG;
-    VO_CUDA(ctx, cudaSetDevice(ctx->device));
-    VO_TRY(vo_reserve(ctx, ctx->d_scratch[1], 256));
-    unsigned long long* d = (unsigned long long*)ctx->d_scratch[1].p;
-    VO_CUDA(ctx, cudaMemsetAsync(d, 0, 24, ctx->stream));
-    pnp_pretest_check_kernel<<<blocks, 256, 0, ctx->stream>>>(seed, per_thread, K[0], K[4], K[2], K[5], reproj_err * reproj_err, depth_lo,
-                                                              depth_hi, d);
-    ctx->launches++;
-    VO_CUDA(ctx, cudaGetLastError());
-    VO_CUDA(ctx, cudaMemcpyAsync(tally, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
-    VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return 0;
-}

@@ -24,7 +24,7 @@
 #define KNN_THREADS (64 + 32 * KNN_EPI_WARPS)
 #define KNN_A_BYTES (KNN_BM * KNN_DIM * 2)        // 32 KB
 #define KNN_B_BYTES (KNN_BN * KNN_DIM * 2)        // 64 KB per stage
-#define KNN_SMEM (1024 + KNN_A_BYTES + 2 * KNN_B_BYTES + 2 * KNN_BN * 4 + 256 + KNN_BM * 4 * 4)   // barriers live in the first 128 B of the 256-B block
+#define KNN_SMEM (1024 + KNN_A_BYTES + 2 * KNN_B_BYTES + 2 * KNN_BN * 4 + 256 + KNN_BM * 4 * 8)   // barriers live in the first 128 B of the 256-B block
 #define KNN_BIG 3.0e38f
 
 // ------------------------------------------------------------------ PTX wrappers (TMA/mbarrier: tma.cuh)
@@ -277,6 +277,15 @@ __device__ __forceinline__ void tc_ld_wait16(uint32_t* v)
                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
                  :: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait32(uint32_t* v)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
     float d;
@@ -297,7 +306,6 @@ knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     const uint32_t sB = base + KNN_A_BYTES;
     const uint32_t sTn = sB + 2 * KNN_B_BYTES;
     const uint32_t sBar = sTn + 2 * KNN_BN * 4;
-    float* tn_s = reinterpret_cast<float*>(smem_raw + (sTn - smem_u32(smem_raw)));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 128 - smem_u32(smem_raw)));
     float* tau_s = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));   // [128 rows][4 column groups]
     const uint32_t bar_a = sBar, bar_bfull = sBar + 8, bar_bempty = sBar + 24, bar_accfull = sBar + 40, bar_accempty = sBar + 56,
@@ -374,50 +382,69 @@ knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             }
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; four warps per lane quadrant, each
-        // scanning one 64-column group of every accumulator tile; one query row per thread.
+        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; four warps per lane quadrant, each scanning one
+        // 64-column group of every accumulator tile as two 32-column pieces; one query row per thread.  The pieces form
+        // ONE software pipeline across tiles and segments: while a piece is scanned the next one's tcgen05.ld is in
+        // flight, and the TMEM stage is handed back to the MMA as soon as its second piece sits in registers.  No CTA-wide
+        // barrier: |t|^2 comes straight from global memory (1 KB per tile, L1-resident, every lane of a warp reads the same
+        // address) and the row's running bound is shared through tagged shared-memory words that may be stale (a stale bound
+        // is only weaker).
         const int q = warp & 3;
         const int sub = (warp - 2) >> 2;          // column group 0..3
         const int rl = q * 32 + lane;             // row inside the tile
-        const int et = (warp - 2) * 32 + lane;    // 0..511
-        if (et < KNN_BN) tn_s[et] = tnorm[(f0 % n_tiles) * KNN_BN + et];
-        int it = 0;
-        for (int f = f0; f < f1;) {
+        // [128 rows][4 groups] {running second-best, segment} as ONE 64-bit word each: value and tag must be read and written
+        // together (a bound paired with another segment's tag belongs to a different query row)
+        volatile unsigned long long* tau_v = reinterpret_cast<volatile unsigned long long*>(tau_s);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64);
+        uint32_t va[32], vb[32];
+        int it = 0, seg = 0;
+        {   // first piece of the first tile
+            mbar_wait(bar_accfull, 0);
+            tc_fence_after();
+            tc_ld32(lane_base, va);
+        }
+        for (int f = f0; f < f1; ++seg) {
             const int m = f / n_tiles, na = f - m * n_tiles, nb = min(n_tiles, na + (f1 - f));
             const int row = m * KNN_BM + rl;
             // ordering uses d' = |t|^2 - 2 q.t (|q|^2 is constant per row and added at the end); exact integers in fp32
             float b1 = KNN_BIG, b2 = KNN_BIG;
             int i1 = -1, i2 = -1;
-            tau_s[rl * 4 + sub] = KNN_BIG;
+            tau_v[rl * 4 + sub] = 0xFFFFFFFF00000000ull;     // nothing to share yet in this segment (tag in the high word)
             for (int n = na; n < nb; ++n, ++it) {
-                const int s = it & 1, ph = (it >> 1) & 1;
-                const int j0 = n * KNN_BN;
-                float tn_next = 0.f;
-                const int n_next = n + 1 < nb ? n + 1 : 0;                  // a following segment starts at train tile 0
-                const bool pre = et < KNN_BN && f + (n - na) + 1 < f1;
-                if (pre) tn_next = tnorm[n_next * KNN_BN + et];             // in flight while this tile is scanned
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                {   // the four warps of a row share their running second-best: anything strictly above the
-                    // smallest of them cannot enter the global top-2 (entries lowered this way carry index -1)
-                    const float4 t4 = *reinterpret_cast<const float4*>(tau_s + rl * 4);
-                    const float tau = fminf(fminf(t4.x, t4.y), fminf(t4.z, t4.w)) + 1.0f;   // integers: next value up
+                const int s = it & 1;
+                const int j0 = n * KNN_BN + sub * 64;
+                {   // the four warps of a row share their running second-best: anything strictly above the smallest of
+                    // them cannot enter the global top-2 (entries lowered this way carry index -1)
+                    float tau = KNN_BIG;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const unsigned long long e = tau_v[rl * 4 + g];
+                        if ((uint32_t)(e >> 32) == (uint32_t)seg) tau = fminf(tau, __uint_as_float((uint32_t)e));
+                    }
+                    tau += 1.0f;                                   // integers: next value up
                     if (tau < b2) { b2 = tau; i2 = -1; }
                 }
-                mbar_wait(bar_accfull + 8 * s, ph);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * KNN_BN + sub * 64);
-                uint32_t va[16], vb[16];
-                tc_ld16(taddr, va);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t* v = (c & 1) ? vb : va;
-                    tc_ld_wait16(v);
-                    if (c + 1 < 4) tc_ld16(taddr + (c + 1) * 16, (c & 1) ? va : vb);
-                    const float4* tn4 = reinterpret_cast<const float4*>(tn_s + s * KNN_BN + sub * 64 + c * 16);
-                    const int jc = j0 + sub * 64 + c * 16;
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t* v = c ? vb : va;
+                    tc_ld_wait32(v);
+                    if (c == 0) {
+                        tc_ld32(lane_base + (uint32_t)(s * KNN_BN + 32), vb);        // second piece of this tile
+                    } else {
+                        tc_fence_before();
+                        mbar_arrive(bar_accempty + 8 * s);                            // both pieces are in registers
+                        if (f + (n - na) + 1 < f1) {                                  // first piece of the next tile
+                            const int it2 = it + 1, s2 = it2 & 1, ph2 = (it2 >> 1) & 1;
+                            mbar_wait(bar_accfull + 8 * s2, ph2);
+                            tc_fence_after();
+                            tc_ld32(lane_base + (uint32_t)(s2 * KNN_BN), va);
+                        }
+                    }
+                    const float4* tn4 = reinterpret_cast<const float4*>(tnorm + j0 + c * 32);
+                    const int jc = j0 + c * 32;
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const float4 ta = tn4[2 * g], tb = tn4[2 * g + 1];
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 ta = __ldg(tn4 + 2 * g), tb = __ldg(tn4 + 2 * g + 1);
                         float dd[8];
                         dd[0] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 0]), ta.x);
                         dd[1] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 1]), ta.y);
@@ -444,10 +471,7 @@ knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
                         }
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(bar_accempty + 8 * s);
-                tau_s[rl * 4 + sub] = b2;
-                if (pre) tn_s[(s ^ 1) * KNN_BN + et] = tn_next;
+                tau_v[rl * 4 + sub] = ((unsigned long long)(uint32_t)seg << 32) | __float_as_uint(b2);
             }
             const float qn = qnorm[row];
             KnnPartial p;

@@ -95,40 +95,6 @@ __device__ __forceinline__ bool pnp_is_inlier(const double* h, double fx, double
     return e <= thr_sq;                              // NaN compares false
 }
 
-// Float32 pre-test of the same decision with a rigorous error bound; 0 = outlier, 1 = inlier, -1 = too close to the
-// threshold to call (the caller then evaluates pnp_is_inlier).  The FP64 pipe of this part issues 32 lanes per clock
-// and SM against 128 for FP32, and the exact form needs a double-precision division, so scoring 32 hypotheses on a
-// thousand points was the longest phase of the fused kernel (30 us of 130).
-//   hf[0..11] = the hypothesis rounded to float, hf[12] = max |t_k|.  With m = |X| + |Y| + |Z| + max|t| every component
-//   of R X + t computed in float (three FMAs on rounded inputs) is within d = 8 ulp(1) m of the exact value; that
-//   becomes du <= fx (d / |z|) (1 + |x / z|) on the projection (+ a few ulps of |u| for the remaining operations and
-//   the rounded intrinsics), and 2 (|dx| du + |dy| dv) + du^2 + dv^2 on the squared residual.  The band is four times
-//   that bound; depths within 100 d of zero are left to the exact form.
-__device__ __forceinline__ int pnp_inlier_pretest(const float* hf, float fx, float fy, float cx, float cy, float X, float Y, float Z,
-                                                  float iu, float iv, float thr_sq)
-{
-    const float x = fmaf(hf[0], X, fmaf(hf[1], Y, fmaf(hf[2], Z, hf[9])));
-    const float y = fmaf(hf[3], X, fmaf(hf[4], Y, fmaf(hf[5], Z, hf[10])));
-    const float z = fmaf(hf[6], X, fmaf(hf[7], Y, fmaf(hf[8], Z, hf[11])));
-    const float m = fabsf(X) + fabsf(Y) + fabsf(Z) + hf[12];
-    const float d = 1.0e-6f * m;                       // > 8 * 2^-24 * m * (1 + rounding of the sum)
-    const float az = fabsf(z);
-    if (!(az > 100.f * d)) return -1;                  // also catches NaN and z == 0
-    const float iz = 1.0f / z;
-    const float xz = x * iz, yz = y * iz;
-    const float u = fmaf(xz, fx, cx), v = fmaf(yz, fy, cy);
-    const float rho = d / az * 1.02f;                  // relative perturbation of 1/z (|d z / z| <= 0.01)
-    const float du = fx * rho * (1.f + fabsf(xz)) + 6.0e-7f * (fabsf(u) + fabsf(cx)) + 1.0e-6f;
-    const float dv = fy * rho * (1.f + fabsf(yz)) + 6.0e-7f * (fabsf(v) + fabsf(cy)) + 1.0e-6f;
-    const float dx = iu - u, dy = iv - v;
-    const float e = fmaf(dx, dx, dy * dy);
-    const float B = 2.f * (fabsf(dx) * du + fabsf(dy) * dv) + du * du + dv * dv + 1.0e-6f * e;
-    const float band = 4.f * B;
-    if (e + band < thr_sq) return 1;
-    if (e - band > thr_sq) return 0;
-    return -1;                                         // NaN lands here too
-}
-
 // Head chunk bookkeeping: the LAST CTA of a sequence to finish (ticket counter, no waiting) replays
 // cv2's loop over the head hypotheses; what it leaves in `niters` bounds every later replay, so
 // the tail launches skip hypotheses >= need[b] (typically all of them: at 10 % outliers cv2 itself
@@ -722,10 +688,10 @@ pnp_epnp_kernel(PnpArgs a)
 // round trips between them (250 us -> one launch), which is what bounds a single sequence and small shards.
 #define FUSED_T EPNP_T
 #define FUSED_CHUNK 32
+#define FUSED_SUB 8       // hypotheses scored between two looks at the adaptive stop
 #define FUSED_WIN 256     // raw RNG values looked at per sampling pass
 
 struct PoseFusedShared {
-    float hf[FUSED_CHUNK * 16];     // the chunk's hypotheses rounded to float (+ max |t|) for the scoring pre-test
     double h[FUSED_CHUNK * 12];
     double rv[FUSED_CHUNK * 3];
     double win_h[12], win_rv[3];
@@ -865,64 +831,54 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
             int okh = 0;
             if (h < nh && F.smp[4 * h] >= 0) okh = pnp_solve_one(a, obj, img, F.smp + 4 * h, F.h + 12 * h, F.rv + 3 * h);
             F.ok[h] = okh;
-            if (okh) {
-                float tm = 0.f;
-                for (int k = 0; k < 12; ++k) F.hf[16 * h + k] = (float)F.h[12 * h + k];
-                for (int k = 9; k < 12; ++k) tm = fmaxf(tm, fabsf((float)F.h[12 * h + k]) * 1.0000002f);
-                F.hf[16 * h + 12] = tm;
-            }
         }
         __syncthreads();
         phase_stamp(a, b, 10);   // (last chunk) minimal solves done
-        if (N > 4) {
-            for (int base = 0; base < N; base += FUSED_T) {
-                const int i = base + tid;
-                const bool live = i < N;
-                float Xf = 0, Yf = 0, Zf = 1, iu = 0, iv = 0;
-                if (live) { Xf = obj[3 * i]; Yf = obj[3 * i + 1]; Zf = obj[3 * i + 2]; iu = img[2 * i]; iv = img[2 * i + 1]; }
-                const float fxf = (float)a.fx, fyf = (float)a.fy, cxf = (float)a.cx, cyf = (float)a.cy;
-                // four hypotheses per pass: four independent dependency chains per lane (the CTA has only two warps per
-                // scheduler, so one chain at a time left the FP32 pipe idle on latency)
-                for (int h0 = 0; h0 < nh; h0 += 4) {
-                    int t[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int h = h0 + k;
-                        const bool on = h < nh && F.ok[h];      // block-uniform
-                        t[k] = (on && live) ? pnp_inlier_pretest(F.hf + 16 * (on ? h : 0), fxf, fyf, cxf, cyf, Xf, Yf, Zf, iu, iv, a.thr_sq) : 0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int h = h0 + k;
-                        if (h >= nh || !F.ok[h]) continue;     // block-uniform
-                        if (t[k] < 0)
-                            t[k] = pnp_is_inlier(F.h + h * 12, a.fx, a.fy, a.cx, a.cy, (double)Xf, (double)Yf, (double)Zf, iu, iv, a.thr_sq) ? 1 : 0;
-                        const unsigned m = __ballot_sync(0xffffffffu, t[k] == 1);
+        // Score eight hypotheses at a time and let thread 0 replay cv2's loop after each eight: cv2 itself stops after
+        // ~5 iterations at 10 % outliers, so the usual frame scores 8 hypotheses instead of 32 (the 32 minimal solves run
+        // in parallel and cost the latency of one; scoring is what an SM with eight warps is slow at: 31 us for 32).
+        for (int h_lo = 0; h_lo < nh; h_lo += FUSED_SUB) {
+            const int h_hi = min(h_lo + FUSED_SUB, nh);
+            if (N > 4) {
+                for (int base = 0; base < N; base += FUSED_T) {
+                    const int i = base + tid;
+                    const bool live = i < N;
+                    double X = 0, Y = 0, Z = 0;
+                    float iu = 0, iv = 0;
+                    if (live) { X = obj[3 * i]; Y = obj[3 * i + 1]; Z = obj[3 * i + 2]; iu = img[2 * i]; iv = img[2 * i + 1]; }
+                    // (a float32 pre-test with an error band was tried here: 33 us against 31 us for this exact form on 1000
+                    // points x 32 hypotheses -- with eight warps on the SM the phase is bound by issue latency, not by the FP64 pipe)
+                    for (int h = h_lo; h < h_hi; ++h) {
+                        if (!F.ok[h]) continue;   // block-uniform
+                        const bool in = live && pnp_is_inlier(F.h + h * 12, a.fx, a.fy, a.cx, a.cy, X, Y, Z, iu, iv, a.thr_sq);
+                        const unsigned m = __ballot_sync(0xffffffffu, in);
                         if (lane == 0 && m) atomicAdd(&F.cnt[h], __popc(m));
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
-        }
-        phase_stamp(a, b, 11);   // (last chunk) scoring done
-        if (tid == 0) {
-            int niters = F.niters, max_good = F.max_good, win = F.win;
-            if (N == 4) { win = F.ok[0] ? 0 : -1; if (win == 0) { for (int k = 0; k < 12; ++k) F.win_h[k] = F.h[k]; for (int k = 0; k < 3; ++k) F.win_rv[k] = F.rv[k]; } }
-            else {
-                for (int h = 0; h < nh && it0 + h < niters; ++h) {
-                    if (!F.ok[h]) continue;
-                    const int good = F.cnt[h];
-                    if (good > (max_good > 3 ? max_good : 3)) {
-                        win = it0 + h; max_good = good;
-                        niters = ransac_update_num_iters(a.conf, (double)(N - good) / N, 4, niters);
-                        for (int k = 0; k < 12; ++k) F.win_h[k] = F.h[12 * h + k];
-                        for (int k = 0; k < 3; ++k) F.win_rv[k] = F.rv[3 * h + k];
+            if (tid == 0) {
+                int niters = F.niters, max_good = F.max_good, win = F.win;
+                if (N == 4) { win = F.ok[0] ? 0 : -1; if (win == 0) { for (int k = 0; k < 12; ++k) F.win_h[k] = F.h[k]; for (int k = 0; k < 3; ++k) F.win_rv[k] = F.rv[k]; } }
+                else {
+                    for (int h = h_lo; h < h_hi && it0 + h < niters; ++h) {
+                        if (!F.ok[h]) continue;
+                        const int good = F.cnt[h];
+                        if (good > (max_good > 3 ? max_good : 3)) {
+                            win = it0 + h; max_good = good;
+                            niters = ransac_update_num_iters(a.conf, (double)(N - good) / N, 4, niters);
+                            for (int k = 0; k < 12; ++k) F.win_h[k] = F.h[12 * h + k];
+                            for (int k = 0; k < 3; ++k) F.win_rv[k] = F.rv[3 * h + k];
+                        }
                     }
                 }
+                F.niters = niters; F.max_good = max_good; F.win = win;
+                if (h_hi == nh || it0 + h_hi >= niters) F.it0 = it0 + nh;     // this chunk is finished (or the loop is)
             }
-            F.niters = niters; F.max_good = max_good; F.win = win; F.it0 = it0 + nh;
+            __syncthreads();
+            if (it0 + h_hi >= F.niters) break;       // block-uniform: the replay can no longer reach the rest of the chunk
         }
-        __syncthreads();
+        phase_stamp(a, b, 11);   // (last chunk) scoring + replay done
     }
 
     phase_stamp(a, b, 2);   // RANSAC chunks done
@@ -977,55 +933,6 @@ pnp_fused_kernel(PnpArgs a, PoseBatchIO io)
         for (int k = tid; k < M; k += FUSED_T) mo[orig[inl[k]]] = 1;
         if (tid == 0) { io.n_inl_out[b] = M; io.ok_out[b] = win >= 0 ? 1 : 0; }
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// self-check of the float pre-test (tests/test_pnp_gpu.py): random poses, landmarks and image points whose squared
-// residual sits at thr (1 +- eps), eps log-uniform in [1e-7, 1e-1] -- far denser around the threshold than any real
-// frame -- classified by pnp_inlier_pretest and by the exact pnp_is_inlier.  tally[0] = trials, [1] = decided by the
-// pre-test, [2] = decided AND different from the exact decision (must be 0).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double u01(unsigned long long& st)
-{
-    st ^= st << 13; st ^= st >> 7; st ^= st << 17;
-    return (double)(st >> 11) * (1.0 / 9007199254740992.0);
-}
-
-__global__ void __launch_bounds__(256)
-pnp_pretest_check_kernel(unsigned long long seed, int per_thread, double fx, double fy, double cx, double cy, float thr_sq,
-                         double depth_lo, double depth_hi, unsigned long long* tally)
-{
-    unsigned long long st = seed * 0x9E3779B97F4A7C15ull + (blockIdx.x * 256ull + threadIdx.x + 1) * 0xD1B54A32D192ED03ull;
-    for (int k = 0; k < 4; ++k) u01(st);
-    unsigned long long n = 0, decided = 0, wrong = 0;
-    for (int it = 0; it < per_thread; ++it) {
-        double rv[3] = {(u01(st) - 0.5) * 1.2, (u01(st) - 0.5) * 1.2, (u01(st) - 0.5) * 1.2}, h[12];
-        rodrigues_to_R(rv, h);
-        const double scale = u01(st) < 0.5 ? 1.0 : 30.0;       // small and large translations (cancellation in R X + t)
-        for (int k = 0; k < 3; ++k) h[9 + k] = (u01(st) - 0.5) * 20.0 * scale;
-        // a landmark in front of the camera: camera-frame point, back to the world frame (rounded to float like real input)
-        const double zc = depth_lo + (depth_hi - depth_lo) * u01(st) * u01(st);
-        const double xc = (u01(st) - 0.5) * 1.6 * zc, yc = (u01(st) - 0.5) * 0.6 * zc;
-        const double pc[3] = {xc - h[9], yc - h[10], zc - h[11]};
-        const float X = (float)(h[0] * pc[0] + h[3] * pc[1] + h[6] * pc[2]);
-        const float Y = (float)(h[1] * pc[0] + h[4] * pc[1] + h[7] * pc[2]);
-        const float Z = (float)(h[2] * pc[0] + h[5] * pc[1] + h[8] * pc[2]);
-        double u, v;
-        project_pt(h, h + 9, fx, fy, cx, cy, (double)X, (double)Y, (double)Z, u, v);
-        const double eps = exp(-16.0 * u01(st) - 2.3) * (u01(st) < 0.5 ? -1.0 : 1.0);
-        const double r = sqrt((double)thr_sq * (1.0 + eps)), ang = 6.283185307179586 * u01(st);
-        const float iu = (float)(u + r * cos(ang)), iv = (float)(v + r * sin(ang));
-        float hf[16];
-        float tm = 0.f;
-        for (int k = 0; k < 12; ++k) hf[k] = (float)h[k];
-        for (int k = 9; k < 12; ++k) tm = fmaxf(tm, fabsf((float)h[k]) * 1.0000002f);
-        hf[12] = tm;
-        const int t = pnp_inlier_pretest(hf, (float)fx, (float)fy, (float)cx, (float)cy, X, Y, Z, iu, iv, thr_sq);
-        const bool ex = pnp_is_inlier(h, fx, fy, cx, cy, (double)X, (double)Y, (double)Z, iu, iv, thr_sq);
-        ++n;
-        if (t >= 0) { ++decided; if ((t == 1) != ex) ++wrong; }
-    }
-    atomicAdd(tally, n); atomicAdd(tally + 1, decided); atomicAdd(tally + 2, wrong);
 }
 
 // ------------------------------------------------------------------------------------------
