@@ -92,7 +92,8 @@ def main():
         ctx.sync()
         r["dev_call_ms"] = e0.elapsed_time(e1) / args.reps
         r["dev_call_what"] = "b200vo_knn2_ratio_dev: f32->f16 prep x2, tcgen05 GEMM + top-2, finalize (CUDA events, back to back)"
-        assert np.array_equal(oi.cpu().numpy(), pi) and np.array_equal(oa.cpu().numpy(), pa)
+        if not os.environ.get("B200VO_KNN_DBG"):      # the kernel's debug modes (TMEM-read / MMA floors) give no results
+            assert np.array_equal(oi.cpu().numpy(), pi) and np.array_equal(oa.cpu().numpy(), pa)
         for ptr in (p0, p1, p2, p3, p4):
             ctx.lib.b200vo_host_free(ctx.h, ptr)
         print(json.dumps(r))

@@ -284,14 +284,14 @@ extern "C" int b200vo_batch_submit_frames_dev(b200vo_batch* B, const uint8_t* fr
 // copy engine arbitrates between streams per copy, not in enqueue order, and a 30 MB frame copy
 // slipping in between the point arrays holds the step's first kernel back by the whole copy
 // (measured: 0.6 ms instead of 0.06 ms for the uploads).
-static int batch_issue_prefetch(b200vo_batch* B, cudaEvent_t after = nullptr)
+static int batch_issue_prefetch(b200vo_batch* B, cudaEvent_t after = nullptr, bool wait_step_end = true)
 {
     b200vo_ctx* ctx = B->ctx;
     const size_t fb = (size_t)B->cfg.rows * B->cfg.cols, total = fb * B->batch;
     for (int k = 0; k < B->q_count; ++k) {
         const int slot = (B->q_head + k) & 1;
         if (!B->q_src[slot]) continue;
-        VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->step_end_ev, 0));   // readers of this set have retired
+        if (wait_step_end) VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->step_end_ev, 0));   // readers of this set have retired
         if (after) VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, after, 0));  // and the step's own uploads have landed
         const uint8_t* raw = B->q_src[slot];
         if (!B->q_dev[slot]) {
@@ -590,8 +590,18 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     VO_CUDA(ctx, upload(o_lmo, lm_obj, (size_t)nb * L * 12, B->io_stream));
     VO_CUDA(ctx, cudaEventRecord(B->obj_ev, B->io_stream));
     }
+    // Small (packed) steps are latency-bound: the copy + pyramid launches of the NEXT frame set (a dozen driver calls)
+    // are enqueued after this step's own kernels instead of in front of them.  The side stream must still wait for the
+    // PREVIOUS step's end only (the set it overwrites was that step's `cur`), so that wait is enqueued here, before
+    // batch_finish re-records the event.
+    bool deferred_prefetch = false;
     if (prefetched) {
-        VO_TRY(batch_issue_prefetch(B, B->done_ev));             // frames of later steps: behind this step's uploads
+        if (packed) {
+            for (int k = 0; k < B->q_count; ++k) deferred_prefetch = deferred_prefetch || B->q_src[(B->q_head + k) & 1] != nullptr;
+            if (deferred_prefetch) VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->step_end_ev, 0));
+        } else {
+            VO_TRY(batch_issue_prefetch(B, B->done_ev));         // frames of later steps: behind this step's uploads
+        }
         VO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B->q_ev[q_slot], 0));
     }
     uint8_t* dq = (uint8_t*)B->outs.p;
@@ -670,6 +680,7 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     if (packed) {
         VO_CUDA(ctx, cudaMemcpyAsync(ho, dq, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        if (deferred_prefetch) VO_TRY(batch_issue_prefetch(B, B->done_ev, false));
         VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
         for (auto& o : outs)

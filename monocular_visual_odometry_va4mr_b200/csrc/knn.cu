@@ -296,8 +296,10 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
                           const float* __restrict__ qnorm, const float* __restrict__ tnorm, int n_tiles, int per, int total,
-                          KnnPartial* __restrict__ partial, int nq_pad)
+                          KnnPartial* __restrict__ partial, int nq_pad, int dbg)
 {
+    // dbg (benchmarks only, B200VO_KNN_DBG): 1 = the epilogue pulls the accumulators but does not scan them (TMEM-read
+    // floor), 2 = it hands every accumulator stage straight back (TMA + MMA floor); results are meaningless then
     extern __shared__ uint8_t smem_raw[];
     const int f0 = blockIdx.x * per, f1 = min(f0 + per, total);
     if (f0 >= f1) return;                      // uniform: before any barrier / TMEM allocation
@@ -327,6 +329,9 @@ knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // every shared bound starts as "tag = no segment": shared memory keeps what the previous CTA on this SM left there, and a
+    // warp that is ahead of its row's other warps would otherwise take a stale {bound, tag 0} of some other query row
+    if (threadIdx.x < KNN_BM * 4) reinterpret_cast<unsigned long long*>(tau_s)[threadIdx.x] = 0xFFFFFFFF00000000ull;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -398,6 +403,14 @@ knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64);
         uint32_t va[32], vb[32];
         int it = 0, seg = 0;
+        if (dbg == 2) {
+            for (int i = 0; i < f1 - f0; ++i) {
+                mbar_wait(bar_accfull + 8 * (i & 1), (i >> 1) & 1);
+                tc_fence_after();
+                tc_fence_before();
+                mbar_arrive(bar_accempty + 8 * (i & 1));
+            }
+        } else {
         {   // first piece of the first tile
             mbar_wait(bar_accfull, 0);
             tc_fence_after();
@@ -442,6 +455,13 @@ knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
                     }
                     const float4* tn4 = reinterpret_cast<const float4*>(tnorm + j0 + c * 32);
                     const int jc = j0 + c * 32;
+                    if (dbg == 1) {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) x ^= v[e];
+                        if (x == 0x7fc12345u) i1 = (int)x;      // keeps the loads alive
+                        continue;
+                    }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float4 ta = __ldg(tn4 + 2 * g), tb = __ldg(tn4 + 2 * g + 1);
@@ -482,6 +502,7 @@ knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             partial[((size_t)slot * 4 + sub) * nq_pad + row] = p;
             f += nb - na;
         }
+        }   // dbg != 2
     }
     tc_fence_before();
     __syncthreads();
@@ -590,8 +611,11 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
         knn_gemm_top2_kernel<<<dim3(m_tiles, n_splits), KNN_THREADS, KNN_SMEM, ctx->stream>>>(map_q, map_t, qn, tn, n_tiles,
                                                                                            tiles_per_split, part, nq_pad);
     else
+    {
+        static const int dbg = getenv("B200VO_KNN_DBG") ? atoi(getenv("B200VO_KNN_DBG")) : 0;
         knn_gemm_top2_flat_kernel<<<(total + per - 1) / per, KNN_THREADS, KNN_SMEM, ctx->stream>>>(map_q, map_t, qn, tn, n_tiles, per,
-                                                                                                total, part, nq_pad);
+                                                                                                total, part, nq_pad, dbg);
+    }
     knn_finalize_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(part, n_splits, nq, nq_pad, nt, ratio, idx2_dev, dist2_dev, accept_dev);
     ctx->launches += 2;
     VO_CUDA(ctx, cudaGetLastError());
