@@ -24,7 +24,7 @@
 #define KNN_THREADS (64 + 32 * KNN_EPI_WARPS)
 #define KNN_A_BYTES (KNN_BM * KNN_DIM * 2)        // 32 KB
 #define KNN_B_BYTES (KNN_BN * KNN_DIM * 2)        // 64 KB per stage
-#define KNN_SMEM (1024 + KNN_A_BYTES + 2 * KNN_B_BYTES + 2 * KNN_BN * 4 + 256 + KNN_BM * 4 * 8)   // barriers live in the first 128 B of the 256-B block
+#define KNN_SMEM (1024 + KNN_A_BYTES + 2 * KNN_B_BYTES + 2 * KNN_BN * 4 + 256 + KNN_BM * 4 * 4)   // barriers live in the first 128 B of the 256-B block
 #define KNN_BIG 3.0e38f
 
 // ------------------------------------------------------------------ PTX wrappers (TMA/mbarrier: tma.cuh)
@@ -254,264 +254,6 @@ knn_gemm_top2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
 }
 
-// ------------------------------------------------------------------ GEMM + fused top-2, flat tile schedule
-// Round 2: (1) the (query tile, train tile) space is cut into one contiguous run per SM (m-major), so all 148 SMs work
-// (the first kernel's grid was m_tiles x floor(SMs / m_tiles) = 128 CTAs at 8192 x 8192); a run may cross into the next
-// query tile: the A tile is reloaded (bar_a / bar_aempty) and the rows' partial top-2 go to the CTA's slot of that tile;
-// (2) the epilogue pulls the accumulator in 16-column pieces with the NEXT piece's tcgen05.ld in flight while the
-// current one is scanned (one wait per piece, issued before the following load), and (3) pre-tests eight distances at
-// a time with three-input minima (FMNMX3).
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v)
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-}
-// wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above the wait
-__device__ __forceinline__ void tc_ld_wait16(uint32_t* v)
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-                 :: "memory");
-}
-__device__ __forceinline__ void tc_ld_wait32(uint32_t* v)
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
-                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
-                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-                 :: "memory");
-}
-__device__ __forceinline__ float fmin3(float a, float b, float c)
-{
-    float d;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
-
-__global__ void __launch_bounds__(KNN_THREADS, 1)
-knn_gemm_top2_flat_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
-                          const float* __restrict__ qnorm, const float* __restrict__ tnorm, int n_tiles, int per, int total,
-                          KnnPartial* __restrict__ partial, int nq_pad, int dbg)
-{
-    // dbg (benchmarks only, B200VO_KNN_DBG): 1 = the epilogue pulls the accumulators but does not scan them (TMEM-read
-    // floor), 2 = it hands every accumulator stage straight back (TMA + MMA floor); results are meaningless then
-    extern __shared__ uint8_t smem_raw[];
-    const int f0 = blockIdx.x * per, f1 = min(f0 + per, total);
-    if (f0 >= f1) return;                      // uniform: before any barrier / TMEM allocation
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sA = base;
-    const uint32_t sB = base + KNN_A_BYTES;
-    const uint32_t sTn = sB + 2 * KNN_B_BYTES;
-    const uint32_t sBar = sTn + 2 * KNN_BN * 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 128 - smem_u32(smem_raw)));
-    float* tau_s = reinterpret_cast<float*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));   // [128 rows][4 column groups]
-    const uint32_t bar_a = sBar, bar_bfull = sBar + 8, bar_bempty = sBar + 24, bar_accfull = sBar + 40, bar_accempty = sBar + 56,
-                   bar_aempty = sBar + 72;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        mbar_init(bar_a, 1);
-        mbar_init(bar_aempty, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_bfull + 8 * s, 1);
-            mbar_init(bar_bempty + 8 * s, 1);
-            mbar_init(bar_accfull + 8 * s, 1);
-            mbar_init(bar_accempty + 8 * s, 32 * KNN_EPI_WARPS);
-        }
-        mbar_fence_init();
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // every shared bound starts as "tag = no segment": shared memory keeps what the previous CTA on this SM left there, and a
-    // warp that is ahead of its row's other warps would otherwise take a stale {bound, tag 0} of some other query row
-    if (threadIdx.x < KNN_BM * 4) reinterpret_cast<unsigned long long*>(tau_s)[threadIdx.x] = 0xFFFFFFFF00000000ull;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int it = 0, seg = 0;
-            for (int f = f0; f < f1; ++seg) {
-                const int m = f / n_tiles, na = f - m * n_tiles, nb = min(n_tiles, na + (f1 - f));
-                mbar_wait(bar_aempty, (seg & 1) ^ 1);            // the previous segment's MMAs have read the old A tile
-                mbar_expect_tx(bar_a, KNN_A_BYTES);
-                tma_load_2d(sA, &map_q, 0, m * KNN_BM, bar_a);
-                tma_load_2d(sA + KNN_A_BYTES / 2, &map_q, 64, m * KNN_BM, bar_a);
-                for (int n = na; n < nb; ++n, ++it) {
-                    const int s = it & 1, ph = (it >> 1) & 1;
-                    mbar_wait(bar_bempty + 8 * s, ph ^ 1);
-                    mbar_expect_tx(bar_bfull + 8 * s, KNN_B_BYTES);
-                    const uint32_t dst = sB + s * KNN_B_BYTES;
-                    tma_load_2d(dst, &map_t, 0, n * KNN_BN, bar_bfull + 8 * s);
-                    tma_load_2d(dst + KNN_B_BYTES / 2, &map_t, 64, n * KNN_BN, bar_bfull + 8 * s);
-                }
-                f += nb - na;
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D=F32, A=B=F16, K-major both, N=256, M=128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(KNN_BN >> 3) << 17) | ((uint32_t)(KNN_BM >> 4) << 24);
-            int it = 0, seg = 0;
-            for (int f = f0; f < f1; ++seg) {
-                const int m = f / n_tiles, na = f - m * n_tiles, nb = min(n_tiles, na + (f1 - f));
-                mbar_wait(bar_a, seg & 1);
-                for (int n = na; n < nb; ++n, ++it) {
-                    const int s = it & 1, ph = (it >> 1) & 1;
-                    mbar_wait(bar_accempty + 8 * s, ph ^ 1);
-                    mbar_wait(bar_bfull + 8 * s, ph);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(s * KNN_BN);
-#pragma unroll
-                    for (int kb = 0; kb < 2; ++kb) {
-                        const uint64_t adesc = umma_desc_sw128(sA + kb * (KNN_A_BYTES / 2));
-                        const uint64_t bdesc = umma_desc_sw128(sB + s * KNN_B_BYTES + kb * (KNN_B_BYTES / 2));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)   // 16 fp16 = 32 B per UMMA_K step inside the swizzle atom
-                            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    tc_commit(bar_bempty + 8 * s);     // smem stage free once these MMAs have read it
-                    tc_commit(bar_accfull + 8 * s);    // accumulator ready for the epilogue
-                }
-                tc_commit(bar_aempty);                 // every MMA of this segment has read the A tile
-                f += nb - na;
-            }
-        }
-    } else {
-        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; four warps per lane quadrant, each scanning one
-        // 64-column group of every accumulator tile as two 32-column pieces; one query row per thread.  The pieces form
-        // ONE software pipeline across tiles and segments: while a piece is scanned the next one's tcgen05.ld is in
-        // flight, and the TMEM stage is handed back to the MMA as soon as its second piece sits in registers.  No CTA-wide
-        // barrier: |t|^2 comes straight from global memory (1 KB per tile, L1-resident, every lane of a warp reads the same
-        // address) and the row's running bound is shared through tagged shared-memory words that may be stale (a stale bound
-        // is only weaker).
-        const int q = warp & 3;
-        const int sub = (warp - 2) >> 2;          // column group 0..3
-        const int rl = q * 32 + lane;             // row inside the tile
-        // [128 rows][4 groups] {running second-best, segment} as ONE 64-bit word each: value and tag must be read and written
-        // together (a bound paired with another segment's tag belongs to a different query row)
-        volatile unsigned long long* tau_v = reinterpret_cast<volatile unsigned long long*>(tau_s);
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64);
-        uint32_t va[32], vb[32];
-        int it = 0, seg = 0;
-        if (dbg == 2) {
-            for (int i = 0; i < f1 - f0; ++i) {
-                mbar_wait(bar_accfull + 8 * (i & 1), (i >> 1) & 1);
-                tc_fence_after();
-                tc_fence_before();
-                mbar_arrive(bar_accempty + 8 * (i & 1));
-            }
-        } else {
-        {   // first piece of the first tile
-            mbar_wait(bar_accfull, 0);
-            tc_fence_after();
-            tc_ld32(lane_base, va);
-        }
-        for (int f = f0; f < f1; ++seg) {
-            const int m = f / n_tiles, na = f - m * n_tiles, nb = min(n_tiles, na + (f1 - f));
-            const int row = m * KNN_BM + rl;
-            // ordering uses d' = |t|^2 - 2 q.t (|q|^2 is constant per row and added at the end); exact integers in fp32
-            float b1 = KNN_BIG, b2 = KNN_BIG;
-            int i1 = -1, i2 = -1;
-            tau_v[rl * 4 + sub] = 0xFFFFFFFF00000000ull;     // nothing to share yet in this segment (tag in the high word)
-            for (int n = na; n < nb; ++n, ++it) {
-                const int s = it & 1;
-                const int j0 = n * KNN_BN + sub * 64;
-                {   // the four warps of a row share their running second-best: anything strictly above the smallest of
-                    // them cannot enter the global top-2 (entries lowered this way carry index -1)
-                    float tau = KNN_BIG;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const unsigned long long e = tau_v[rl * 4 + g];
-                        if ((uint32_t)(e >> 32) == (uint32_t)seg) tau = fminf(tau, __uint_as_float((uint32_t)e));
-                    }
-                    tau += 1.0f;                                   // integers: next value up
-                    if (tau < b2) { b2 = tau; i2 = -1; }
-                }
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t* v = c ? vb : va;
-                    tc_ld_wait32(v);
-                    if (c == 0) {
-                        tc_ld32(lane_base + (uint32_t)(s * KNN_BN + 32), vb);        // second piece of this tile
-                    } else {
-                        tc_fence_before();
-                        mbar_arrive(bar_accempty + 8 * s);                            // both pieces are in registers
-                        if (f + (n - na) + 1 < f1) {                                  // first piece of the next tile
-                            const int it2 = it + 1, s2 = it2 & 1, ph2 = (it2 >> 1) & 1;
-                            mbar_wait(bar_accfull + 8 * s2, ph2);
-                            tc_fence_after();
-                            tc_ld32(lane_base + (uint32_t)(s2 * KNN_BN), va);
-                        }
-                    }
-                    const float4* tn4 = reinterpret_cast<const float4*>(tnorm + j0 + c * 32);
-                    const int jc = j0 + c * 32;
-                    if (dbg == 1) {
-                        uint32_t x = 0;
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) x ^= v[e];
-                        if (x == 0x7fc12345u) i1 = (int)x;      // keeps the loads alive
-                        continue;
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float4 ta = __ldg(tn4 + 2 * g), tb = __ldg(tn4 + 2 * g + 1);
-                        float dd[8];
-                        dd[0] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 0]), ta.x);
-                        dd[1] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 1]), ta.y);
-                        dd[2] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 2]), ta.z);
-                        dd[3] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 3]), ta.w);
-                        dd[4] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 4]), tb.x);
-                        dd[5] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 5]), tb.y);
-                        dd[6] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 6]), tb.z);
-                        dd[7] = __fmaf_rn(-2.f, __uint_as_float(v[g * 8 + 7]), tb.w);
-                        const float mn = fmin3(fmin3(dd[0], dd[1], dd[2]), fmin3(dd[3], dd[4], dd[5]), fminf(dd[6], dd[7]));
-                        if (mn < b2) {   // some element of this group of eight displaces the running second-best
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float d = dd[e];
-                                if (d < b2) {
-                                    const int j = jc + g * 8 + e;
-                                    const bool lt1 = d < b1;           // strict: ascending j, the lower train index wins ties
-                                    i2 = lt1 ? i1 : j;
-                                    b2 = lt1 ? b1 : d;
-                                    i1 = lt1 ? j : i1;
-                                    b1 = lt1 ? d : b1;
-                                }
-                            }
-                        }
-                    }
-                }
-                tau_v[rl * 4 + sub] = ((unsigned long long)(uint32_t)seg << 32) | __float_as_uint(b2);
-            }
-            const float qn = qnorm[row];
-            KnnPartial p;
-            p.d1 = i1 >= 0 ? __fadd_rn(b1, qn) : KNN_BIG;
-            p.d2 = i2 >= 0 ? __fadd_rn(b2, qn) : KNN_BIG;
-            p.i1 = i1; p.i2 = i2;
-            const int slot = (int)blockIdx.x - (m * n_tiles) / per;       // this CTA's position among those sharing query tile m
-            partial[((size_t)slot * 4 + sub) * nq_pad + row] = p;
-            f += nb - na;
-        }
-        }   // dbg != 2
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-    }
-}
-
 // merge the per-range partial top-2s in train-index order, take square roots, apply the ratio test
 __global__ void __launch_bounds__(256)
 knn_finalize_kernel(const KnnPartial* __restrict__ partial, int n_splits, int nq, int nq_pad, int nt, double ratio,
@@ -562,25 +304,12 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
 {
     const int nq_pad = (int)vo_align((size_t)nq, KNN_BM), nt_pad = (int)vo_align((size_t)nt, KNN_BN);
     const int m_tiles = nq_pad / KNN_BM, n_tiles = nt_pad / KNN_BN;
-    // B200VO_KNN=flat selects the flat schedule (one contiguous run of (query tile, train tile) pairs per SM, all 148
-    // SMs busy); measured at 8192 x 8192 (profiles/r2d_knn_*): 39.1 us against 34.4 us for the first kernel
-    // (m_tiles x floor(SMs / m_tiles) = 128 CTAs) -- its 16-column epilogue pieces expose the TMEM load latency four
-    // times per tile instead of twice -- so the first kernel stays the default until the flat one wins
-    static const bool use_v1 = !(getenv("B200VO_KNN") && !strcmp(getenv("B200VO_KNN"), "flat"));
-    const int total = m_tiles * n_tiles;
-    const int per = (total + ctx->num_sms - 1) / ctx->num_sms;
-    int n_splits;
-    int tiles_per_split = 0;
-    if (use_v1) {
-        // split the train range so that the grid covers the SMs; every split keeps tiles in ascending order
-        n_splits = ctx->num_sms / m_tiles;   // one wave: m_tiles * n_splits <= number of SMs
-        if (n_splits > n_tiles) n_splits = n_tiles;
-        if (n_splits < 1) n_splits = 1;
-        tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
-        n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-    } else {
-        n_splits = (n_tiles + per - 1) / per + 1;   // CTAs that can share one query tile
-    }
+    // split the train range so that the grid covers the SMs; every split keeps tiles in ascending order
+    int n_splits = ctx->num_sms / m_tiles;   // one wave: m_tiles * n_splits <= number of SMs
+    if (n_splits > n_tiles) n_splits = n_tiles;
+    if (n_splits < 1) n_splits = 1;
+    const int tiles_per_split = (n_tiles + n_splits - 1) / n_splits;
+    n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const size_t b_q16 = vo_align((size_t)nq_pad * KNN_DIM * 2, 1024), b_t16 = vo_align((size_t)nt_pad * KNN_DIM * 2, 1024);
     const size_t b_qn = vo_align((size_t)nq_pad * 4, 256), b_tn = vo_align((size_t)nt_pad * 4, 256);
     const size_t b_part = vo_align((size_t)4 * n_splits * nq_pad * sizeof(KnnPartial), 256);
@@ -594,7 +323,6 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
     int* bad = (int*)d;
     ctx->knn_bad_flag = bad;
     VO_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
-    if (!use_v1) VO_CUDA(ctx, cudaMemsetAsync(part, 0xFF, b_part, ctx->stream));   // slots no CTA writes: index -1 = "no entry"
     knn_prep_kernel<<<(nq_pad + 7) / 8, 256, 0, ctx->stream>>>(q_dev, nq, nq_pad, q16, qn, 0.f, bad);
     knn_prep_kernel<<<(nt_pad + 7) / 8, 256, 0, ctx->stream>>>(t_dev, nt, nt_pad, t16, tn, KNN_BIG, bad);
     ctx->launches += 2;
@@ -604,18 +332,10 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
     static bool attr_done = false;
     if (!attr_done) {
         VO_CUDA(ctx, cudaFuncSetAttribute(knn_gemm_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNN_SMEM));
-        VO_CUDA(ctx, cudaFuncSetAttribute(knn_gemm_top2_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KNN_SMEM));
         attr_done = true;
     }
-    if (use_v1)
-        knn_gemm_top2_kernel<<<dim3(m_tiles, n_splits), KNN_THREADS, KNN_SMEM, ctx->stream>>>(map_q, map_t, qn, tn, n_tiles,
-                                                                                           tiles_per_split, part, nq_pad);
-    else
-    {
-        static const int dbg = getenv("B200VO_KNN_DBG") ? atoi(getenv("B200VO_KNN_DBG")) : 0;
-        knn_gemm_top2_flat_kernel<<<(total + per - 1) / per, KNN_THREADS, KNN_SMEM, ctx->stream>>>(map_q, map_t, qn, tn, n_tiles, per,
-                                                                                                total, part, nq_pad, dbg);
-    }
+    knn_gemm_top2_kernel<<<dim3(m_tiles, n_splits), KNN_THREADS, KNN_SMEM, ctx->stream>>>(map_q, map_t, qn, tn, n_tiles, tiles_per_split,
+                                                                                       part, nq_pad);
     knn_finalize_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(part, n_splits, nq, nq_pad, nt, ratio, idx2_dev, dist2_dev, accept_dev);
     ctx->launches += 2;
     VO_CUDA(ctx, cudaGetLastError());
