@@ -96,6 +96,15 @@ void orc_decompose_essential(const double E[9], double R1[9], double R2[9], doub
 int orc_recover_pose(const double E[9], const float* p1, const float* p2, int n, const double K[9],
                      double dist_thresh, double R[9], double t[3], uint8_t* mask, int* n_good);
 
+/* ---- f4, ref :35, :226-227: cv2.SIFT_create().detectAndCompute(img, None), default parameters (sift_oracle.c) ----
+ * kps: max_kp x {x, y, size, angle, response, octave (int32 bits)}, desc: max_kp x 128 (may be NULL); returns the number
+ * of keypoints found, in cv2's order (removeDuplicatedSorted); only the first max_kp are written. */
+int orc_sift_detect_and_compute(const uint8_t* img, int rows, int cols, size_t step, int max_kp, float* kps, float* desc);
+int orc_sift_gauss_image(const uint8_t* img, int rows, int cols, size_t step, int octave, int layer, float* out, int* orows, int* ocols);
+int orc_gaussian_kernel_f32(double sigma, float* k, int max_n);
+void orc_gaussian_blur_f32(const float* src, int rows, int cols, double sigma, float* dst);
+float orc_fast_atan2_deg(float y, float x);
+
 #ifdef __cplusplus
 }
 #endif

@@ -207,7 +207,24 @@ def emat():
     np.savez_compressed(os.path.join(OUT, "emat.npz"), **out)
 
 
-ALL = dict(klt_small=klt_small, pnp=pnp, gftt=gftt, knn=knn, emat=emat)
+def sift():
+    """cv2.SIFT_create().detectAndCompute(img, None) (reference :35, :226-227) on three small synthetic frames: keypoints
+    (x, y, size, angle, response), packed octave codes, descriptors (integer-valued, stored as uint8)."""
+    out = {}
+    for ci, (shape, seed, w, h) in enumerate((("kitti", 2, 416, 160), ("parking", 1, 320, 240), ("malaga", 4, 257, 193))):
+        img = synth.render_sequence(shape, 1, seed=seed, width=w, height=h)["frames"][0]
+        kps, des = cv2.SIFT_create().detectAndCompute(img, None)
+        out[f"c{ci}_img"] = img
+        out[f"c{ci}_kp"] = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in kps], np.float32)
+        out[f"c{ci}_octave"] = np.array([k.octave for k in kps], np.int32)
+        assert np.array_equal(des, np.round(des)) and des.min() >= 0 and des.max() <= 255
+        out[f"c{ci}_desc"] = des.astype(np.uint8)
+    out["n_cases"] = np.array(3)
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(os.path.join(OUT, "sift.npz"), **out)
+
+
+ALL = dict(klt_small=klt_small, pnp=pnp, gftt=gftt, knn=knn, emat=emat, sift=sift)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(ALL)
