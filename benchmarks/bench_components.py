@@ -2,7 +2,7 @@
 """Secondary workloads of BASELINE.json (configs 2-4): per call-site timings through the C-ABI
 (host buffers in, host buffers out) next to the same cv2 call on the host cores.
 
-  python benchmarks/bench_components.py [--only knn,gftt,klt,pnp,emat,next] [--reps 20]
+  python benchmarks/bench_components.py [--only knn,gftt,klt,pnp,emat,next,sift] [--reps 20]
 
 Prints one JSON object per workload.  `gpu_ms` is CUDA-event time on the ctx stream for the whole
 call (H2D + kernels + D2H), `wall_ms` the median wall clock of the call, `cv2_ms` the median wall
@@ -34,7 +34,7 @@ def med(f, reps, warm=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="knn,gftt,klt,pnp,emat,next")
+    ap.add_argument("--only", default="knn,gftt,klt,pnp,emat,next,sift")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--no-cv2", action="store_true")
     args = ap.parse_args()
@@ -97,6 +97,18 @@ def main():
         for ptr in (p0, p1, p2, p3, p4):
             ctx.lib.b200vo_host_free(ctx.h, ptr)
         print(json.dumps(r))
+    if "sift" in only:      # the bootstrap's detectAndCompute (reference :226-227)
+        for shape in ("kitti", "parking", "malaga"):
+            f = synth.render_sequence(shape, 1, seed=0)["frames"][0]
+            kp, octv, des = cv2_compat.sift_detect_and_compute(f)
+            wall = med(lambda: cv2_compat.sift_detect_and_compute(f), args.reps)
+            r = {"workload": f"SIFT detectAndCompute {f.shape[1]}x{f.shape[0]} ({shape}-shaped)", "keypoints": int(len(kp)), "wall_ms": wall,
+                 "gpu_ms": ctx.last_gpu_ms()}
+            if cv2 is not None:
+                sift = cv2.SIFT_create()
+                r["cv2_ms"] = med(lambda: sift.detectAndCompute(f, None), 5, 1)
+                r["cv2_keypoints"] = len(sift.detectAndCompute(f, None)[0])
+            print(json.dumps(r))
     if "gftt" in only:
         f = synth.render_sequence("kitti", 1, seed=0)["frames"][0]
         wall = med(lambda: cv2_compat.goodFeaturesToTrack(f, 1400, 0.1, 10, blockSize=3), args.reps)

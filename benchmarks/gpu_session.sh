@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-T=r2l
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/${T}_bench_n2.json 2> gpurun_out/${T}_bench_n2.err; echo "n2 rc=$?"; tail -3 gpurun_out/${T}_bench_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 20 --warmup 5 > gpurun_out/${T}_bench_n2_ref.json 2> gpurun_out/${T}_bench_n2_ref.err; echo "n2 ref rc=$?"; tail -3 gpurun_out/${T}_bench_n2_ref.err
+T=r2m
+timeout 900 python -m pytest tests/test_sift_gpu.py -m gpu -q -x > gpurun_out/${T}_pytest_sift.log 2>&1; echo "pytest sift rc=$?"; tail -30 gpurun_out/${T}_pytest_sift.log
+python benchmarks/bench_components.py --only sift --reps 10 > gpurun_out/${T}_sift.jsonl 2>&1; cat gpurun_out/${T}_sift.jsonl

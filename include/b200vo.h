@@ -204,6 +204,16 @@ int b200vo_recover_pose(b200vo_ctx* ctx, const double E[9], const float* p1, con
                         uint8_t* mask, int* n_good);
 
 /*
+ * Replaces cv2.SIFT_create().detectAndCompute(img, None) at :35, :226-227 (default parameters:
+ * nfeatures 0, nOctaveLayers 3, contrastThreshold 0.04, edgeThreshold 10, sigma 1.6, image doubled, float32 descriptors).
+ * img uint8 (rows, cols), `step` bytes per row.  kps float32 (max_kp, 6): x, y, size, angle, response and the bits of
+ * cv2's packed int32 `octave` field, in cv2's output order (KeyPointsFilter::removeDuplicatedSorted); desc float32
+ * (max_kp, 128), integer-valued 0..255, or NULL.  *n_out = keypoints found; only the first max_kp are written.
+ */
+int b200vo_sift_detect_and_compute(b200vo_ctx* ctx, const uint8_t* img, int rows, int cols, size_t step, int max_kp,
+                                   float* kps, float* desc, int32_t* n_out);
+
+/*
  * Replaces cv2.solvePnPRansac(obj, img, K, zeros(4), flags=SOLVEPNP_P3P, confidence=,
  * reprojectionError=, iterationsCount=) at :343 (incl. cv2's EPnP refit on the inliers).
  * obj float32 (n,3), img float32 (n,2).  inliers int32 (n) caller-allocated, ascending,

@@ -75,6 +75,7 @@ SIGNATURES = {
         C.c_void_p]),
     "b200vo_debug_pose_phases": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p, C.c_int, C.c_float, C.c_double, C.POINTER(C.c_longlong), c_f32p]),
+    "b200vo_sift_detect_and_compute": (C.c_int, [C.c_void_p, c_u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, c_f32p, c_f32p, c_i32p]),
     "b200vo_recover_pose": (C.c_int, [C.c_void_p, c_f64p, c_f32p, c_f32p, C.c_int, c_f64p, C.c_double, c_f64p, c_f64p, c_u8p, c_intp]),
     "b200vo_min_distance_mask": (C.c_int, [C.c_void_p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_float, c_u8p]),
     "b200vo_triangulate_landmarks": (C.c_int, [

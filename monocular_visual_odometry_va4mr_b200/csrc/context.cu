@@ -90,6 +90,7 @@ extern "C" void b200vo_destroy(b200vo_ctx* ctx)
     for (auto& b : ctx->d_scratch) if (b.p) cudaFree(b.p);
     for (auto& s : ctx->slots) if (s.slab.p) cudaFree(s.slab.p);
     if (ctx->d_rng.p) cudaFree(ctx->d_rng.p);
+    if (ctx->d_sift.p) cudaFree(ctx->d_sift.p);
     if (ctx->d_klt_queue.p) cudaFree(ctx->d_klt_queue.p);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     cudaEventDestroy(ctx->ev0);

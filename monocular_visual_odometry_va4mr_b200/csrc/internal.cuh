@@ -65,6 +65,7 @@ struct b200vo_ctx {
     int* knn_bad_flag = nullptr;   // device flag of the last kNN call (inside d_scratch[3])
     DevBuf d_klt_queue;      // ring of work-queue counters for the persistent tracker kernel
     unsigned klt_queue_next = 0;
+    DevBuf d_sift;           // SIFT scale-space workspace (sift.cu)
     DevBuf d_rng;            // raw cv::RNG stream (uint32)
     int n_rng = 0;
     // tensor-map encode entry point (driver API, fetched lazily)

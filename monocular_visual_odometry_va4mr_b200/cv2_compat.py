@@ -245,6 +245,69 @@ class BFMatcher:
 
 
 # --------------------------------------------------------------------------------------
+# cv2.SIFT_create().detectAndCompute  (reference :35, :226-227)
+# --------------------------------------------------------------------------------------
+class KeyPoint:
+    """Field-compatible with cv2.KeyPoint (the reference reads .pt, :232-233)."""
+    __slots__ = ("pt", "size", "angle", "response", "octave", "class_id")
+
+    def __init__(self, x=0.0, y=0.0, size=0.0, angle=-1.0, response=0.0, octave=0, class_id=-1):
+        self.pt, self.size, self.angle, self.response, self.octave, self.class_id = (x, y), size, angle, response, octave, class_id
+
+    def __repr__(self):
+        return f"KeyPoint(pt={self.pt}, size={self.size}, angle={self.angle}, octave={self.octave})"
+
+
+def sift_detect_and_compute(image, max_keypoints=1 << 17):
+    """Array form: (kp float32 (n, 5) = x, y, size, angle, response; octave int32 (n,); descriptors float32 (n, 128)),
+    rows in cv2's output order."""
+    img, step = _image_arg(image, "SIFT.detectAndCompute image")
+    ctx = _ctx()
+    rows, cols = img.shape
+    cap = 8192
+    while True:
+        kps = np.empty((cap, 6), np.float32)
+        desc = np.empty((cap, 128), np.float32)
+        n = C.c_int32(0)
+        rc = ctx.lib.b200vo_sift_detect_and_compute(ctx.h, _p(img, c_u8p), rows, cols, step, cap, _p(kps, c_f32p), _p(desc, c_f32p), C.byref(n))
+        if rc != 0:
+            _raise(ctx, rc, "SIFT.detectAndCompute")
+        if n.value <= cap or cap >= max_keypoints:
+            break
+        cap = min(max_keypoints, max(n.value, 2 * cap))      # rare: more keypoints than the first buffer holds
+    m = min(n.value, cap)
+    return kps[:m, :5].copy(), kps[:m, 5].copy().view(np.int32), desc[:m].copy()
+
+
+class SIFT:
+    """cv2.SIFT_create() with the default parameters, as the reference constructs it (:35)."""
+
+    def __init__(self, nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, enable_precise_upscale=False):
+        if (nfeatures, nOctaveLayers, float(contrastThreshold), float(edgeThreshold), float(sigma), bool(enable_precise_upscale)) != (0, 3, 0.04, 10.0, 1.6, False):
+            raise NotImplementedError("b200vo SIFT: only cv2.SIFT_create()'s default parameters (the reference's call)")
+
+    def detectAndCompute(self, image, mask, descriptors=None, useProvidedKeypoints=False):
+        if mask is not None or useProvidedKeypoints:
+            raise NotImplementedError("b200vo SIFT.detectAndCompute: mask / useProvidedKeypoints are not supported (the reference passes None)")
+        kp, octave, desc = sift_detect_and_compute(image)
+        if _cv2 is not None:        # real cv2.KeyPoint objects when cv2 is there (drawKeypoints etc. keep working)
+            kps = tuple(_cv2.KeyPoint(float(r[0]), float(r[1]), float(r[2]), float(r[3]), float(r[4]), int(o), -1) for r, o in zip(kp, octave))
+        else:
+            kps = tuple(KeyPoint(float(r[0]), float(r[1]), float(r[2]), float(r[3]), float(r[4]), int(o)) for r, o in zip(kp, octave))
+        return kps, (desc if len(desc) else None)
+
+    def descriptorSize(self):
+        return 128
+
+    def defaultNorm(self):
+        return NORM_L2
+
+
+def SIFT_create(*args, **kwargs):
+    return SIFT(*args, **kwargs)
+
+
+# --------------------------------------------------------------------------------------
 # cv2.findEssentialMat  (reference :308)
 # --------------------------------------------------------------------------------------
 def findEssentialMat(points1, points2, cameraMatrix=None, method=RANSAC, prob=0.999, threshold=1.0,
@@ -336,7 +399,7 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs, rvec=Non
 # --------------------------------------------------------------------------------------
 # installation onto the real cv2 module (route (i) of SURVEY.md 8b)
 # --------------------------------------------------------------------------------------
-_PATCHED = ("calcOpticalFlowPyrLK", "goodFeaturesToTrack", "BFMatcher", "findEssentialMat", "solvePnPRansac", "recoverPose")
+_PATCHED = ("calcOpticalFlowPyrLK", "goodFeaturesToTrack", "BFMatcher", "findEssentialMat", "solvePnPRansac", "recoverPose", "SIFT_create")
 _saved: dict = {}
 
 
@@ -360,7 +423,7 @@ def uninstall(cv2_module=None):
 
 
 def __getattr__(name):
-    """Anything that is not on the hot path (SIFT_create, recoverPose, Rodrigues, ...) is the real cv2's."""
+    """Anything that is not on the hot path (Rodrigues, triangulatePoints, ...) is the real cv2's."""
     if _cv2 is not None and hasattr(_cv2, name):
         return getattr(_cv2, name)
     raise AttributeError(name)

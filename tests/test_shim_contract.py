@@ -80,11 +80,11 @@ def test_cv2_assertion_conditions_raise_cv2_style_errors():
     assert cv2_compat.findEssentialMat(np.zeros((4, 2), np.float32), np.zeros((4, 2), np.float32), np.eye(3)) == (None, None)
 
 
-def test_install_patches_and_restores_six_names():
+def test_install_patches_and_restores_seven_names():
     cv2 = pytest.importorskip("cv2")
-    names = ("calcOpticalFlowPyrLK", "goodFeaturesToTrack", "BFMatcher", "findEssentialMat", "recoverPose", "solvePnPRansac")
+    names = ("calcOpticalFlowPyrLK", "goodFeaturesToTrack", "BFMatcher", "findEssentialMat", "recoverPose", "solvePnPRansac", "SIFT_create")
     orig = {n: getattr(cv2, n) for n in names}
-    untouched = {n: getattr(cv2, n) for n in ("SIFT_create", "triangulatePoints", "Rodrigues", "pyrDown")}
+    untouched = {n: getattr(cv2, n) for n in ("triangulatePoints", "Rodrigues", "pyrDown")}
     try:
         cv2_compat.install()
         for n in names:
