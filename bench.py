@@ -584,7 +584,7 @@ def measure_single(args, opts, ctx, W):
 
 
 def klt_roofline(args, opts, wl, res, roofline_note):
-    """Roofline of the dominant kernel (the LANDMARK launch of klt_kernel_v2), timed live with CUDA events on the
+    """Roofline of the dominant kernel (the LANDMARK launch of klt_kernel_v3), timed live with CUDA events on the
     stream it is launched on (b200vo_batch_profile)."""
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -606,7 +606,7 @@ def klt_roofline(args, opts, wl, res, roofline_note):
         tj = json.load(open(tpath))
         if tj.get("workload") == {"shape": args.shape, "batch": wl.batch, "landmarks": args.landmarks, "candidates": args.candidates}:
             traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
-    return {"bound": "hbm", "kernel": "klt_kernel_v2 (landmark launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    return {"bound": "hbm", "kernel": "klt_kernel_v3 (landmark launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": klt_bytes, "avg_launch_ms": klt_ms,
             "stage_ms_per_step": {"pyramid": float(res["stage_ms"][0]) / nprof, "klt_landmarks": klt_ms,
@@ -614,7 +614,7 @@ def klt_roofline(args, opts, wl, res, roofline_note):
             "note": roofline_note}, levels
 
 
-ROOFLINE_NOTE = ("klt_kernel_v2 is instruction-issue bound (integer bilinear taps from shared-memory-staged windows, ~25 window passes per "
+ROOFLINE_NOTE = ("klt_kernel_v3 is instruction-issue bound (integer bilinear taps from shared-memory-staged windows, ~25 window passes per "
                  "point); its DRAM traffic ~ the algorithmic bytes, so the HBM fraction stays at percent level by construction; see DESIGN.md section 4")
 
 

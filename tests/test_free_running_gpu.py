@@ -99,3 +99,29 @@ def test_free_running_pipeline_on_cuda_path():
         assert np.abs(R - Rr).max() < 2e-3 and np.abs(t - tr_).max() < 2e-2 * max(1.0, np.abs(tr_).max()), (i, np.abs(R - Rr).max(), np.abs(t - tr_).max())
     print("free-running num_pts", vo.num_pts, "reference", ref,
           "max pose dev", max(np.abs(vo.poses[i] - g[f"tri{i}_cur"]).max() for i in range(n)))
+
+
+def test_bootstrap_from_raw_frames_on_cuda_path():
+    """The whole bootstrap of `initialization` (:293-323) on the CUDA path, starting from the two raw frames:
+    SIFT detectAndCompute x2 (:226-227) -> knnMatch(k=2) + ratio test (:229, :218-224) -> findEssentialMat (:308).
+    The matched point pairs must be the ones the unmodified reference class produced with cv2 (recorded in
+    reference_trace.npz): CUDA SIFT keypoint positions are bit-equal to cv2's and ~99.9 % of the descriptors are identical,
+    so at most a pair or two may differ where one descriptor entry is off by one at a ratio-test tie."""
+    import reference_trace
+    g, frames = reference_trace.load()
+    b0, b1 = (int(v) for v in g["bootstrap"])
+    sift = cv2_compat.SIFT_create()
+    kp0, d0 = sift.detectAndCompute(frames[b0], None)
+    kp1, d1 = sift.detectAndCompute(frames[b1], None)
+    matches = cv2_compat.BFMatcher().knnMatch(d0, d1, k=2)
+    ratio = 0.8                                              # the reference's KITTI option 'feature_ratio' (main.py:28)
+    good = [m for m, n in matches if m.distance < ratio * n.distance]
+    pts0 = np.float32([kp0[m.queryIdx].pt for m in good]).reshape(-1, 2)
+    pts1 = np.float32([kp1[m.trainIdx].pt for m in good]).reshape(-1, 2)
+    want = {tuple(np.r_[a, b].tolist()) for a, b in zip(g["emat0_p1"], g["emat0_p2"])}
+    got = {tuple(np.r_[a, b].tolist()) for a, b in zip(pts0, pts1)}
+    assert abs(len(got) - len(want)) <= max(2, len(want) // 200), (len(got), len(want))
+    assert len(got & want) >= len(want) - max(2, len(want) // 200), (len(got & want), len(want))
+    E, mask = cv2_compat.findEssentialMat(pts0, pts1, g["K"], method=cv2_compat.RANSAC, prob=0.99, threshold=1.0)
+    assert abs(int(mask.sum()) - int(g["num_pts"][0])) <= max(3, 0.01 * int(g["num_pts"][0]))
+    print("bootstrap pairs", len(got), "recorded", len(want), "common", len(got & want), "E inliers", int(mask.sum()), "recorded", int(g["num_pts"][0]))
