@@ -254,16 +254,309 @@ knn_gemm_top2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------ round 2: 256 query rows per CTA, norms inside the GEMM
+// What bounds the kernel above at 8192 x 8192 (measured with its epilogue cut short): the L2 operand
+// feed -- every CTA re-streams the train descriptors, 64 KB per 128 x 256 x 128 tile -- and the scan's instruction count.
+// This kernel (1) keeps TWO query tiles resident per CTA and streams train tiles of 128 rows through a 3-stage ring, so
+// one 36 KB stage feeds two M = 128 MMAs (half the operand bytes per flop); (2) folds the norms into the contraction:
+// the query operand is -2 q with three extra K columns {1, 256, 256}, the train operand is t with {a0, a1, 256 a2}
+// where |t|^2 = a0 + 256 a1 + 65536 a2 (base-256 digits; every operand is an integer fp16 represents exactly, every
+// partial sum an integer below 2^24), so the accumulator IS d' = |t|^2 - 2 q.t and the scan needs neither the FMA nor
+// the |t|^2 loads; the 16 extra K columns travel as their own 32-byte-swizzled TMA boxes and cost one more UMMA_K step
+// (K = 144); (3) spreads (query pair, train tile) units over all SMs in contiguous runs (a run may cross into the next
+// query pair: the A tiles are reloaded and the rows' partial top-2 go to the CTA's slot of that pair); (4) scans in
+// groups of four with a two-instruction minimum and an update path that inserts the group's minimum first.
+#define K3_BN 128
+#define K3_STAGES 3
+#define K3_A_HALF (KNN_BM * KNN_DIM * 2 + KNN_BM * 32)        // 32 KB main + 4 KB extra columns
+#define K3_B_STAGE (K3_BN * KNN_DIM * 2 + K3_BN * 32)         // 32 KB + 4 KB
+#define K3_SMEM (1024 + 2 * K3_A_HALF + K3_STAGES * K3_B_STAGE + 256 + 2 * KNN_BM * 2 * 8)
+
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr)
+{
+    // K-major, 32-byte swizzle: rows of 32 B, 8-row groups 256 B apart
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
+}
+__device__ __forceinline__ void tc_ld_wait32(uint32_t* v)
+{
+    // wait::ld with the loaded registers as in/out operands: nothing that reads them can be scheduled above the wait
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// f32 -> fp16 operands of the kernel below.  query: -2 q | {1, 256, 256, 0 ..}; train: t | {a0, a1, 256 a2, 0 ..}; rows
+// beyond n: zeros | {0, 0, 65504}: d' = 16 769 024 against any query, above every real d' (<= 128 * 255^2)
+__global__ void __launch_bounds__(256)
+knn_prep3_kernel(const float* __restrict__ src, int n, int n_pad, int is_query, __half* __restrict__ dst, __half* __restrict__ ext,
+                 float* __restrict__ norm, int* __restrict__ bad)
+{
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) v = reinterpret_cast<const float4*>(src + (size_t)row * KNN_DIM)[lane];
+    const float a[4] = {v.x, v.y, v.z, v.w};
+    float s = 0.f;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ok = ok && (a[k] >= 0.f) && (a[k] <= 255.f) && (a[k] == floorf(a[k]));
+        s += a[k] * a[k];
+    }
+    const float sc = is_query ? -2.f : 1.f;
+    __half2 h0 = __floats2half2_rn(sc * a[0], sc * a[1]), h1 = __floats2half2_rn(sc * a[2], sc * a[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    reinterpret_cast<uint2*>(dst + (size_t)row * KNN_DIM)[lane] = pk;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // exact: integers < 2^24
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) atomicOr(bad, 1);
+    if (lane == 0 && norm) norm[row] = s;
+    if (lane < 16) {
+        float e = 0.f;
+        if (is_query) e = lane == 0 ? 1.f : (lane < 3 ? 256.f : 0.f);
+        else if (row >= n) e = lane == 2 ? 65504.f : 0.f;
+        else {
+            const int si = ok ? (int)s : 0;
+            e = lane == 0 ? (float)(si & 255) : lane == 1 ? (float)((si >> 8) & 255) : lane == 2 ? (float)((si >> 16) * 256) : 0.f;
+        }
+        ext[(size_t)row * 16 + lane] = __float2half_rn(e);
+    }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS, 1)
+knn_gemm_top2_m256_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qx,
+                          const __grid_constant__ CUtensorMap map_t, const __grid_constant__ CUtensorMap map_tx,
+                          const float* __restrict__ qnorm, int n_tiles, int per, int total, KnnPartial* __restrict__ partial, int nq_pad,
+                          int* __restrict__ gbound)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const int f0 = blockIdx.x * per, f1 = min(f0 + per, total);
+    if (f0 >= f1) return;                      // uniform: before any barrier / TMEM allocation
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base;
+    const uint32_t sB = base + 2 * K3_A_HALF;
+    const uint32_t sBar = sB + K3_STAGES * K3_B_STAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 128 - smem_u32(smem_raw)));
+    // [256 rows][2 column groups] {running second-best, segment tag} as one 64-bit word each
+    volatile unsigned long long* tau_v = reinterpret_cast<volatile unsigned long long*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));
+    const uint32_t bar_a = sBar, bar_aempty = sBar + 8, bar_bfull = sBar + 16, bar_bempty = sBar + 40, bar_accfull = sBar + 64,
+                   bar_accempty = sBar + 80;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+        mbar_init(bar_aempty, 1);
+        for (int s = 0; s < K3_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, 32 * KNN_EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // shared bounds start as "tag = no segment" (shared memory keeps what the previous CTA on this SM left there)
+    if (threadIdx.x < 2 * KNN_BM * 2) tau_v[threadIdx.x] = 0xFFFFFFFF00000000ull;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0, seg = 0;
+            for (int f = f0; f < f1; ++seg) {
+                const int m = f / n_tiles, na = f - m * n_tiles, nb = min(n_tiles, na + (f1 - f));
+                mbar_wait(bar_aempty, (seg & 1) ^ 1);            // the previous segment's MMAs have read the old A tiles
+                mbar_expect_tx(bar_a, 2 * K3_A_HALF);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t dst = sA + h * K3_A_HALF;
+                    const int r0 = m * 2 * KNN_BM + h * KNN_BM;
+                    tma_load_2d(dst, &map_q, 0, r0, bar_a);
+                    tma_load_2d(dst + KNN_BM * 128, &map_q, 64, r0, bar_a);
+                    tma_load_2d(dst + KNN_BM * 256, &map_qx, 0, r0, bar_a);
+                }
+                for (int n = na; n < nb; ++n, ++it) {
+                    const int s = it % K3_STAGES, ph = (it / K3_STAGES) & 1;
+                    mbar_wait(bar_bempty + 8 * s, ph ^ 1);
+                    mbar_expect_tx(bar_bfull + 8 * s, K3_B_STAGE);
+                    const uint32_t dst = sB + s * K3_B_STAGE;
+                    tma_load_2d(dst, &map_t, 0, n * K3_BN, bar_bfull + 8 * s);
+                    tma_load_2d(dst + K3_BN * 128, &map_t, 64, n * K3_BN, bar_bfull + 8 * s);
+                    tma_load_2d(dst + K3_BN * 256, &map_tx, 0, n * K3_BN, bar_bfull + 8 * s);
+                }
+                f += nb - na;
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=F32, A=B=F16, K-major both, N=128, M=128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(K3_BN >> 3) << 17) | ((uint32_t)(KNN_BM >> 4) << 24);
+            int it = 0, seg = 0;
+            for (int f = f0; f < f1; ++seg) {
+                const int m = f / n_tiles, na = f - m * n_tiles, nb = min(n_tiles, na + (f1 - f));
+                mbar_wait(bar_a, seg & 1);
+                for (int n = na; n < nb; ++n, ++it) {
+                    const int s = it % K3_STAGES, ph = (it / K3_STAGES) & 1;
+                    const int as = it & 1, aph = (it >> 1) & 1;
+                    mbar_wait(bar_accempty + 8 * as, aph ^ 1);
+                    mbar_wait(bar_bfull + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sBs = sB + s * K3_B_STAGE;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + h * 128);
+                        const uint32_t sAh = sA + h * K3_A_HALF;
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb) {
+                            const uint64_t adesc = umma_desc_sw128(sAh + kb * (KNN_BM * 128));
+                            const uint64_t bdesc = umma_desc_sw128(sBs + kb * (K3_BN * 128));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)   // 16 fp16 = 32 B per UMMA_K step inside the swizzle atom
+                                tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        tc_mma_f16(d_tmem, umma_desc_sw32(sAh + KNN_BM * 256), umma_desc_sw32(sBs + K3_BN * 256), idesc, 1);   // the norm columns
+                    }
+                    tc_commit(bar_bempty + 8 * s);      // smem stage free once these MMAs have read it
+                    tc_commit(bar_accfull + 8 * as);    // accumulators ready for the epilogue
+                }
+                tc_commit(bar_aempty);                  // every MMA of this segment has read the A tiles
+                f += nb - na;
+            }
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31.  Sixteen warps = 4 lane quadrants x 2 query halves x 2
+        // column groups of 64; one query row per thread.  The accumulator already holds d' = |t|^2 - 2 q.t (|q|^2 is
+        // constant per row and added at the end); exact integers in fp32.
+        const int q = warp & 3;
+        const int idx = (warp - 2) >> 2;
+        const int h = idx >> 1, cg = idx & 1;
+        const int rl = h * KNN_BM + q * 32 + lane;          // row inside the query pair
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 128 + cg * 64);
+        int it = 0, seg = 0;
+        uint32_t va[32], vb[32];
+        {   // first piece of the first unit; from here on the pieces form one software pipeline across units and segments:
+            // while a piece is scanned the next one's tcgen05.ld is in flight
+            mbar_wait(bar_accfull, 0);
+            tc_fence_after();
+            tc_ld32(lane_base, va);
+        }
+        for (int f = f0; f < f1; ++seg) {
+            const int m = f / n_tiles, na = f - m * n_tiles, nb = min(n_tiles, na + (f1 - f));
+            const int row = m * 2 * KNN_BM + rl;
+            float b1 = KNN_BIG, b2 = KNN_BIG;
+            int i1 = -1, i2 = -1;
+            tau_v[rl * 2 + cg] = 0xFFFFFFFF00000000ull;     // nothing to share yet in this segment (tag in the high word)
+            // Every CTA (and warp) that scans other train tiles for this query row publishes its running second-best -- as
+            // the true squared distance, a non-negative float whose bit pattern orders like an int -- in gbound[row].
+            // With a bound from the whole row (4-5 CTAs x 2 warps share a query pair at 8192 x 8192) the update path,
+            // which a warp enters when ANY of its 32 rows is displaced, runs for ~13 % of the groups instead of ~55 %.
+            // Pruning never removes a top-2 entry (the bound is some subset's second-best + 1), so the result does not
+            // depend on who publishes when.
+            const float qn = qnorm[row];
+            float published = KNN_BIG;
+            int gb = 0x7F7F7F7F, gb_next;
+            for (int n = na; n < nb; ++n, ++it) {
+                const int as = it & 1;
+                const int j0 = n * K3_BN + cg * 64;
+                // the row's global bound is read one stage ahead (an L2 round trip): a bound that is one stage old is only weaker
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gb_next) : "l"(gbound + row));
+                {   // the two warps of a row share their running second-best: anything strictly above the smaller of them
+                    // cannot enter the global top-2 (entries lowered this way carry index -1)
+                    const unsigned long long e = tau_v[rl * 2 + (cg ^ 1)];
+                    float tau = KNN_BIG;
+                    if ((uint32_t)(e >> 32) == (uint32_t)seg) tau = __uint_as_float((uint32_t)e);
+                    tau = fminf(tau, __fsub_rn(__int_as_float(gb), qn)) + 1.0f;      // exact integers (or huge); next value up
+                    if (tau < b2) { b2 = tau; i2 = -1; }
+                }
+                tc_ld_wait32(va);
+                tc_ld32(lane_base + (uint32_t)(as * 256 + 32), vb);          // in flight while the first piece is scanned
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t* v = c ? vb : va;
+                    if (c == 1) {
+                        tc_ld_wait32(vb);
+                        tc_fence_before();
+                        mbar_arrive(bar_accempty + 8 * as);                   // both pieces are in registers
+                        if (f + (n - na) + 1 < f1) {                          // first piece of the next unit (this or the next segment)
+                            const int it2 = it + 1;
+                            mbar_wait(bar_accfull + 8 * (it2 & 1), (it2 >> 1) & 1);
+                            tc_fence_after();
+                            tc_ld32(lane_base + (uint32_t)((it2 & 1) * 256), va);
+                        }
+                    }
+                    const int jc = j0 + c * 32;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float d0 = __uint_as_float(v[g * 4 + 0]), d1 = __uint_as_float(v[g * 4 + 1]);
+                        const float d2 = __uint_as_float(v[g * 4 + 2]), d3 = __uint_as_float(v[g * 4 + 3]);
+                        const float mn = fminf(fmin3(d0, d1, d2), d3);
+                        if (mn < b2) {   // some lane's running second-best is displaced inside this group of four
+                            const float dd[4] = {d0, d1, d2, d3};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float d = dd[e];
+                                if (d < b2) {
+                                    const int j = jc + g * 4 + e;
+                                    const bool lt1 = d < b1;           // strict: ascending j, the lower train index wins ties
+                                    i2 = lt1 ? i1 : j;
+                                    b2 = lt1 ? b1 : d;
+                                    i1 = lt1 ? j : i1;
+                                    b1 = lt1 ? d : b1;
+                                }
+                            }
+                        }
+                    }
+                }
+                gb = gb_next;
+                tau_v[rl * 2 + cg] = ((unsigned long long)(uint32_t)seg << 32) | __float_as_uint(b2);
+                {   // a lowered bound (index -1) is some second-best + 1: publish the second-best itself
+                    const float mine = i2 >= 0 ? b2 : b2 - 1.0f;
+                    if (mine < published) {
+                        published = mine;
+                        atomicMin(gbound + row, __float_as_int(__fadd_rn(mine, qn)));
+                    }
+                }
+            }
+            KnnPartial p;
+            p.d1 = i1 >= 0 ? __fadd_rn(b1, qn) : KNN_BIG;
+            p.d2 = i2 >= 0 ? __fadd_rn(b2, qn) : KNN_BIG;
+            p.i1 = i1; p.i2 = i2;
+            const int slot = (int)blockIdx.x - (m * n_tiles) / per;       // this CTA's position among those sharing query pair m
+            partial[((size_t)slot * 2 + cg) * nq_pad + row] = p;
+            f += nb - na;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // merge the per-range partial top-2s in train-index order, take square roots, apply the ratio test
 __global__ void __launch_bounds__(256)
-knn_finalize_kernel(const KnnPartial* __restrict__ partial, int n_splits, int nq, int nq_pad, int nt, double ratio,
+knn_finalize_kernel(const KnnPartial* __restrict__ partial, int n_lists, int nq, int nq_pad, int nt, double ratio,
                     int* __restrict__ idx2, float* __restrict__ dist2, uint8_t* __restrict__ accept)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nq) return;
     float b1 = KNN_BIG, b2 = KNN_BIG;
     int i1 = -1, i2 = -1;
-    for (int s = 0; s < 4 * n_splits; ++s) {
+    for (int s = 0; s < n_lists; ++s) {
         const KnnPartial p = partial[(size_t)s * nq_pad + r];
         const float ds[2] = {p.d1, p.d2};
         const int is[2] = {p.i1, p.i2};
@@ -298,9 +591,17 @@ static int knn_make_map(b200vo_ctx* ctx, CUtensorMap* map, void* gptr, int rows,
     return vo_encode_tiled(ctx, map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, gptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-// device-resident core: q_dev/t_dev float32 row-major; outputs device pointers
-int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* t_dev, int nt, double ratio,
-                      int* idx2_dev, float* dist2_dev, uint8_t* accept_dev, int* bad_flag_host)
+static int knn_make_map_ext(b200vo_ctx* ctx, CUtensorMap* map, void* gptr, int rows, int box_rows)
+{
+    const cuuint64_t dims[2] = {16, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {32};
+    const cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+    return vo_encode_tiled(ctx, map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, gptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// the round-1 kernel (one query tile per CTA, norms added in the scan): B200VO_KNN=v1
+static int vo_knn2_ratio_dev_v1(b200vo_ctx* ctx, const float* q_dev, int nq, const float* t_dev, int nt, double ratio,
+                                int* idx2_dev, float* dist2_dev, uint8_t* accept_dev, int* bad_flag_host)
 {
     const int nq_pad = (int)vo_align((size_t)nq, KNN_BM), nt_pad = (int)vo_align((size_t)nt, KNN_BN);
     const int m_tiles = nq_pad / KNN_BM, n_tiles = nt_pad / KNN_BN;
@@ -336,7 +637,60 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
     }
     knn_gemm_top2_kernel<<<dim3(m_tiles, n_splits), KNN_THREADS, KNN_SMEM, ctx->stream>>>(map_q, map_t, qn, tn, n_tiles, tiles_per_split,
                                                                                        part, nq_pad);
-    knn_finalize_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(part, n_splits, nq, nq_pad, nt, ratio, idx2_dev, dist2_dev, accept_dev);
+    knn_finalize_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(part, 4 * n_splits, nq, nq_pad, nt, ratio, idx2_dev, dist2_dev, accept_dev);
+    ctx->launches += 2;
+    VO_CUDA(ctx, cudaGetLastError());
+    if (bad_flag_host) VO_CUDA(ctx, cudaMemcpyAsync(bad_flag_host, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+// device-resident core: q_dev/t_dev float32 row-major; outputs device pointers
+int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* t_dev, int nt, double ratio,
+                      int* idx2_dev, float* dist2_dev, uint8_t* accept_dev, int* bad_flag_host)
+{
+    static const bool use_v1 = getenv("B200VO_KNN") && !strcmp(getenv("B200VO_KNN"), "v1");
+    if (use_v1) return vo_knn2_ratio_dev_v1(ctx, q_dev, nq, t_dev, nt, ratio, idx2_dev, dist2_dev, accept_dev, bad_flag_host);
+    const int nq_pad = (int)vo_align((size_t)nq, 2 * KNN_BM), nt_pad = (int)vo_align((size_t)nt, K3_BN);
+    const int m_pairs = nq_pad / (2 * KNN_BM), n_tiles = nt_pad / K3_BN;
+    // (query pair, train tile) units in query-pair-major order, one contiguous run per SM
+    const int total = m_pairs * n_tiles;
+    const int per = (total + ctx->num_sms - 1) / ctx->num_sms;
+    const int n_splits = (n_tiles + per - 1) / per + 1;      // CTAs that can share one query pair
+    const size_t b_q16 = vo_align((size_t)nq_pad * KNN_DIM * 2, 1024), b_t16 = vo_align((size_t)nt_pad * KNN_DIM * 2, 1024);
+    const size_t b_qx = vo_align((size_t)nq_pad * 32, 1024), b_tx = vo_align((size_t)nt_pad * 32, 1024);
+    const size_t b_qn = vo_align((size_t)nq_pad * 4, 256);
+    const size_t b_part = vo_align((size_t)2 * n_splits * nq_pad * sizeof(KnnPartial), 256);
+    const size_t b_gb = vo_align((size_t)nq_pad * 4, 256);
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[3], b_q16 + b_t16 + b_qx + b_tx + b_qn + b_part + b_gb + 256));
+    uint8_t* d = (uint8_t*)ctx->d_scratch[3].p;
+    __half* q16 = (__half*)d; d += b_q16;
+    __half* t16 = (__half*)d; d += b_t16;
+    __half* qx = (__half*)d; d += b_qx;
+    __half* tx = (__half*)d; d += b_tx;
+    float* qn = (float*)d; d += b_qn;
+    KnnPartial* part = (KnnPartial*)d; d += b_part;
+    int* gbound = (int*)d; d += b_gb;
+    int* bad = (int*)d;
+    ctx->knn_bad_flag = bad;
+    VO_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
+    VO_CUDA(ctx, cudaMemsetAsync(part, 0xFF, b_part, ctx->stream));   // lists no CTA writes: index -1 = "no entry"
+    VO_CUDA(ctx, cudaMemsetAsync(gbound, 0x7F, b_gb, ctx->stream));   // 0x7F7F7F7F = 3.4e38: no bound yet
+    knn_prep3_kernel<<<(nq_pad + 7) / 8, 256, 0, ctx->stream>>>(q_dev, nq, nq_pad, 1, q16, qx, qn, bad);
+    knn_prep3_kernel<<<(nt_pad + 7) / 8, 256, 0, ctx->stream>>>(t_dev, nt, nt_pad, 0, t16, tx, nullptr, bad);
+    ctx->launches += 2;
+    CUtensorMap map_q, map_t, map_qx, map_tx;
+    VO_TRY(knn_make_map(ctx, &map_q, q16, nq_pad, KNN_BM));
+    VO_TRY(knn_make_map(ctx, &map_t, t16, nt_pad, K3_BN));
+    VO_TRY(knn_make_map_ext(ctx, &map_qx, qx, nq_pad, KNN_BM));
+    VO_TRY(knn_make_map_ext(ctx, &map_tx, tx, nt_pad, K3_BN));
+    static bool attr_done = false;
+    if (!attr_done) {
+        VO_CUDA(ctx, cudaFuncSetAttribute(knn_gemm_top2_m256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM));
+        attr_done = true;
+    }
+    knn_gemm_top2_m256_kernel<<<(total + per - 1) / per, KNN_THREADS, K3_SMEM, ctx->stream>>>(map_q, map_qx, map_t, map_tx, qn, n_tiles, per, total,
+                                                                                               part, nq_pad, gbound);
+    knn_finalize_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(part, 2 * n_splits, nq, nq_pad, nt, ratio, idx2_dev, dist2_dev, accept_dev);
     ctx->launches += 2;
     VO_CUDA(ctx, cudaGetLastError());
     if (bad_flag_host) VO_CUDA(ctx, cudaMemcpyAsync(bad_flag_host, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
