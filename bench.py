@@ -524,6 +524,52 @@ def measure_detect(arm):
     return detect
 
 
+def measure_bootstrap(args):
+    """extra: the bootstrap of `initialization` (reference :293-323) from two raw frames -- SIFT detectAndCompute x2
+    (:226-227), knnMatch(k=2) + ratio test (:229, :218-224), findEssentialMat (:308), recoverPose (:315) -- on the CUDA
+    path through the cv2-shaped shim, and the same calls on cv2.  BASELINE config 2's call chain at the frame's own
+    keypoint count (the 8192 x 8192 matcher stress is benchmarks/bench_components.py)."""
+    import numpy as np
+    from monocular_visual_odometry_va4mr_b200 import cv2_compat, synth, workload
+    shape = args.shape
+    s = synth.render_sequence(shape, 3, seed=2)
+    f0, f1, K = s["frames"][0], s["frames"][2], s["K"]          # main.py:18 bootstrap_frames = [0, 2]
+
+    def chain(m):
+        sift = m.SIFT_create()
+        k0, d0 = sift.detectAndCompute(f0, None)
+        k1, d1 = sift.detectAndCompute(f1, None)
+        matches = m.BFMatcher().knnMatch(d0, d1, k=2)
+        good = [a for a, b in matches if a.distance < 0.8 * b.distance]
+        p0 = np.float32([k0[a.queryIdx].pt for a in good]).reshape(-1, 2)
+        p1 = np.float32([k1[a.trainIdx].pt for a in good]).reshape(-1, 2)
+        E, mask = m.findEssentialMat(p0, p1, K, method=m.RANSAC, prob=0.99, threshold=1.0)
+        n, R, t, _ = m.recoverPose(E, p0[mask.ravel() == 1], p1[mask.ravel() == 1], K)
+        return len(k0), len(k1), len(good), int(mask.sum()), int(n)
+
+    def timed(m, reps):
+        chain(m)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = chain(m)
+        return 1e3 * (time.perf_counter() - t0) / reps, out
+
+    ms, out = timed(cv2_compat, 5)
+    boot = {"ms": ms, "keypoints": list(out[:2]), "ratio_test_survivors": out[2], "essential_inliers": out[3], "recover_pose_good": out[4],
+            "what": f"{shape}-shaped bootstrap from two raw frames: SIFT x2, knnMatch + ratio test, findEssentialMat, recoverPose through cv2_compat "
+                    "(host buffers in and out per call, Python objects for keypoints and matches included)"}
+    if not args.no_cpu_baseline:
+        try:
+            import cv2
+        except ImportError:
+            return boot
+        cv2.setNumThreads(os.cpu_count() or 1)
+        cms, cout = timed(cv2, 2)
+        boot.update(cv2_ms=cms, x_cv2=cms / ms, cv2_counts=list(cout),
+                    cv2_what=f"cv2 {cv2.__version__}, same calls, cv2-internal threading on {os.cpu_count()} cores")
+    return boot
+
+
 def single_plan(K, W):
     """Step counts of the one-sequence extra: (GPU timed steps, cv2 warm-up steps, cv2 timed steps).  Frames are
     addressed with workload.frame_at(), which is defined for every t, so no count can index out of range."""
@@ -695,6 +741,7 @@ def main(argv=None):
     detect = guarded(measure_detect, arm) if solo else None
     arm.close()
     single = guarded(measure_single, args, opts, ctx, W) if solo else None
+    bootstrap = guarded(measure_bootstrap, args) if solo else None
 
     # ---- extra: the other scaling form at N > 1 (at N = 1 the two coincide) ----
     other = None
@@ -742,6 +789,7 @@ def main(argv=None):
             "parity": parity,
             "single_sequence": single,
             "detect": detect,
+            "bootstrap": bootstrap,
             ("weak_scaling" if args.scaling == "strong" else "strong_scaling"): other,
         }
         print(json.dumps(line))

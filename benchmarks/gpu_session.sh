@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
-T=r2s
-timeout 600 python -m pytest tests/test_knn_gpu.py tests/test_dev_api_gpu.py -m gpu -q > gpurun_out/${T}_pytest_knn.log 2>&1; echo "pytest knn rc=$?"; tail -3 gpurun_out/${T}_pytest_knn.log
-ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:knn_gemm --csv --log-file gpurun_out/${T}_knn.csv python benchmarks/bench_components.py --only knn --no-cv2 --reps 1 > /dev/null 2>&1
-grep "m256" gpurun_out/${T}_knn.csv | awk -F'","' '{print $(NF-2), $NF}' | tail -4
+T=r2z
+timeout 900 python -m pytest tests/test_sift_gpu.py -m gpu -q -x > gpurun_out/${T}_pytest_sift.log 2>&1; echo "pytest sift rc=$?"; tail -3 gpurun_out/${T}_pytest_sift.log
+python benchmarks/bench_components.py --only sift --reps 10 --no-cv2 > gpurun_out/${T}_sift.jsonl 2>&1; cat gpurun_out/${T}_sift.jsonl
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sift_desc --csv --log-file gpurun_out/${T}_sift_launches.csv python benchmarks/bench_components.py --only sift --reps 1 --no-cv2 > /dev/null 2>&1
+python profiles/summarize.py launches gpurun_out/${T}_sift_launches.csv 2>&1 | head -4
