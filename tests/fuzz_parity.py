@@ -26,7 +26,7 @@ def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
     rng = np.random.default_rng(int(os.environ.get("FUZZ_SEED", "1")))
     t_end = time.time() + budget
-    stats = dict(klt=0, gftt=0, knn=0, pnp=0, emat=0, rpose=0, mind=0, tri=0)
+    stats = dict(klt=0, gftt=0, knn=0, pnp=0, emat=0, rpose=0, mind=0, tri=0, sift=0)
     bad = []
 
     def rand_frames():
@@ -37,7 +37,7 @@ def main():
     it = 0
     while time.time() < t_end:
         it += 1
-        kind = it % 8
+        kind = it % 9
         try:
             if kind in (0, 1, 2):
                 f0, f1 = rand_frames()["frames"]
@@ -60,6 +60,13 @@ def main():
                 if not (np.array_equal(st, rst) and np.array_equal(p[ok], rp[ok]) and np.array_equal(err[rst == 1], rerr[rst == 1])):
                     bad.append(("klt", (w, h), win, ml, crit, n, int((st != rst).sum()), float(np.abs(p - rp)[ok].max()) if ok.any() else 0))
                 stats["klt"] += 1
+            elif kind == 8:
+                f0 = rand_frames()["frames"][0]
+                a = cv2_compat.sift_detect_and_compute(f0)
+                b = oracle.sift_detect_and_compute(f0)
+                if not all(np.array_equal(x, y) for x, y in zip(a, b)):      # keypoints, octave codes, descriptors: bit for bit
+                    bad.append(("sift", f0.shape, len(a[0]), len(b[0])))
+                stats["sift"] += 1
             elif kind == 3:
                 f0 = rand_frames()["frames"][0]
                 mc = int(rng.choice([0, 50, 1400, 5000]))
