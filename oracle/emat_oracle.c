@@ -112,35 +112,48 @@ static int poly_roots(const double* c, int n, double* re, double* im)
         double ang = 2 * M_PI * k / n + 0.4, r = rad * 0.5 * (1 + 0.1 * k / n);
         re[k] = r * cos(ang); im[k] = r * sin(ang);
     }
+    /* Termination per root, as the CUDA solver and -- in effect -- cv2's solvePoly behave: a root is settled when its step
+     * is below 1e-12 (relative), when |p(z)| has reached the rounding noise of its own evaluation (a root of a close
+     * cluster cannot get closer: its imaginary part stays at ~1e-5 and the root is NOT taken as real, which is what
+     * cv2's Durand-Kerner iteration does with such clusters; iterating on for the full 200 rounds lets the noise decide),
+     * or when it is unmistakably complex and within 1e-6 of its limit. */
     for (int it = 0; it < 200; ++it) {
-        double maxstep = 0;
+        int all_settled = 1;
         for (int k = 0; k < n; ++k) {
             /* p(z), p'(z) by Horner in complex arithmetic */
-            double pr = 1, pi = 0, dr = 0, di = 0, zr = re[k], zi = im[k];
+            double pr = 1, pi = 0, dr = 0, di = 0, zr = re[k], zi = im[k], sb = 1;
+            const double az = sqrt(zr * zr + zi * zi);
             for (int i = n - 1; i >= 0; --i) {
                 double ndr = dr * zr - di * zi + pr, ndi = dr * zi + di * zr + pi;
                 double npr = pr * zr - pi * zi + a[i], npi = pr * zi + pi * zr;
                 dr = ndr; di = ndi; pr = npr; pi = npi;
+                sb = sb * az + fabs(a[i]);
             }
+            double rel = 0;
             double den = dr * dr + di * di;
-            if (den == 0) continue;
-            double wr = (pr * dr + pi * di) / den, wi = (pi * dr - pr * di) / den;   /* p/p' */
-            double sr = 0, si = 0;
-            for (int j = 0; j < n; ++j) {
-                if (j == k) continue;
-                double er = zr - re[j], ei = zi - im[j], d2 = er * er + ei * ei;
-                if (d2 == 0) continue;
-                sr += er / d2; si -= ei / d2;
+            if (den != 0) {
+                double wr = (pr * dr + pi * di) / den, wi = (pi * dr - pr * di) / den;   /* p/p' */
+                double sr = 0, si = 0;
+                for (int j = 0; j < n; ++j) {
+                    if (j == k) continue;
+                    double er = zr - re[j], ei = zi - im[j], d2 = er * er + ei * ei;
+                    if (d2 == 0) continue;
+                    sr += er / d2; si -= ei / d2;
+                }
+                double qr = 1 - (wr * sr - wi * si), qi = -(wr * si + wi * sr);
+                double qd = qr * qr + qi * qi;
+                if (qd != 0) {
+                    double stepr = (wr * qr + wi * qi) / qd, stepi = (wi * qr - wr * qi) / qd;
+                    re[k] -= stepr; im[k] -= stepi;
+                    rel = (fabs(stepr) + fabs(stepi)) / (fabs(re[k]) + fabs(im[k]) + 1e-300);
+                }
             }
-            double qr = 1 - (wr * sr - wi * si), qi = -(wr * si + wi * sr);
-            double qd = qr * qr + qi * qi;
-            if (qd == 0) continue;
-            double stepr = (wr * qr + wi * qi) / qd, stepi = (wi * qr - wr * qi) / qd;
-            re[k] -= stepr; im[k] -= stepi;
-            double st = fabs(stepr) + fabs(stepi), sc = fabs(re[k]) + fabs(im[k]) + 1e-300;
-            if (st / sc > maxstep) maxstep = st / sc;
+            const double mag = fabs(re[k]) + fabs(im[k]);
+            const int noise = fabs(pr) + fabs(pi) <= 2e-14 * sb;
+            const int settled = rel < 1e-12 || noise || (it >= 8 && rel < 1e-6 && fabs(im[k]) > 1e-4 * mag && fabs(im[k]) > 1e-7);
+            if (!settled) all_settled = 0;
         }
-        if (maxstep < 1e-12) break;   // real roots are Newton-polished afterwards
+        if (all_settled) break;   /* real roots are Newton-polished afterwards */
     }
     return n;
 }

@@ -90,7 +90,8 @@ def main():
             elif kind == 5:
                 n, of = int(rng.integers(4, 3000)), float(rng.uniform(0, 0.8))
                 iters, thr = int(rng.choice([100, 500, 2000])), float(rng.choice([8, 5, 2]))
-                obj, img, K = make_pnp_case(n, of, int(rng.integers(0, 10000)))
+                case_seed = int(rng.integers(0, 10000))
+                obj, img, K = make_pnp_case(n, of, case_seed)
                 ok, rv, tv, inl = cv2_compat.solvePnPRansac(obj, img, K, np.zeros(4), flags=cv2_compat.SOLVEPNP_P3P, confidence=0.99,
                                                             reprojectionError=thr, iterationsCount=iters)
                 ro, rrv, rtv, rinl, _ = oracle.solve_pnp_ransac_p3p(obj, img, K, iters, thr, 0.99)
@@ -98,17 +99,19 @@ def main():
                 if same and ok and len(inl) >= 6:       # EPnP on < 6 points is not pinned
                     same = np.abs(rv - rrv).max() < 1e-6 and np.abs(tv - rtv).max() < 1e-6 * max(1, np.abs(rtv).max())
                 if not same:
-                    bad.append(("pnp", n, of, iters, thr))
+                    bad.append(("pnp", n, of, iters, thr, "seed", case_seed))
                 stats["pnp"] += 1
             elif kind == 6:
                 n, of = int(rng.integers(5, 3000)), float(rng.uniform(0, 0.6))
-                p1, p2, K = make_emat_pair(n, of, int(rng.integers(0, 10000)))
+                case_seed = int(rng.integers(0, 10000))
+                p1, p2, K = make_emat_pair(n, of, case_seed)
                 E, m = cv2_compat.findEssentialMat(p1, p2, K, method=cv2_compat.RANSAC, prob=0.99, threshold=1)
                 Eo, mo, _ = oracle.find_essential_mat(p1, p2, K, 0.99, 1.0, 1000)
                 # the CUDA five-point solver (warp-cooperative, Jacobi-style Aberth) and the oracle's (sequential) agree to
-                # ~1e-13 in E: a point whose Sampson error sits within that of the threshold may flip (seen: 1 point in 428 runs)
+                # ~1e-13 in E on well-conditioned samples; a sample whose det B(z) has a close root cluster can give them
+                # different models (~0.1 % of the calls, cv2 itself differs as often)
                 if (E is None) != (Eo is None) or (E is not None and int((m != mo).sum()) > 1):
-                    bad.append(("emat", n, of, None if E is None else int((m != mo).sum())))
+                    bad.append(("emat", n, of, None if E is None else int((m != mo).sum()), "seed", case_seed))
                 elif E is not None:
                     g1, R1, t1, k1 = cv2_compat.recoverPose(E, p1, p2, K)
                     g2, R2, t2, k2 = oracle.recover_pose(E, p1, p2, K)
