@@ -254,23 +254,30 @@ knn_gemm_top2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
 }
 
-// ------------------------------------------------------------------ round 2: 256 query rows per CTA, norms inside the GEMM
+// ------------------------------------------------------------------ round 2: 256 query rows per CTA, distances inside the GEMM
 // What bounds the kernel above at 8192 x 8192 (measured with its epilogue cut short): the L2 operand
-// feed -- every CTA re-streams the train descriptors, 64 KB per 128 x 256 x 128 tile -- and the scan's instruction count.
-// This kernel (1) keeps TWO query tiles resident per CTA and streams train tiles of 128 rows through a 3-stage ring, so
-// one 36 KB stage feeds two M = 128 MMAs (half the operand bytes per flop); (2) folds the norms into the contraction:
-// the query operand is -2 q with three extra K columns {1, 256, 256}, the train operand is t with {a0, a1, 256 a2}
-// where |t|^2 = a0 + 256 a1 + 65536 a2 (base-256 digits; every operand is an integer fp16 represents exactly, every
-// partial sum an integer below 2^24), so the accumulator IS d' = |t|^2 - 2 q.t and the scan needs neither the FMA nor
-// the |t|^2 loads; the 16 extra K columns travel as their own 32-byte-swizzled TMA boxes and cost one more UMMA_K step
-// (K = 144); (3) spreads (query pair, train tile) units over all SMs in contiguous runs (a run may cross into the next
-// query pair: the A tiles are reloaded and the rows' partial top-2 go to the CTA's slot of that pair); (4) scans in
-// groups of four with a two-instruction minimum and an update path that inserts the group's minimum first.
+// feed -- every CTA re-streams the train descriptors, 64 KB per 128 x 256 x 128 tile -- and the scan: a compare-select
+// update path that a warp enters when ANY of its 32 rows is displaced, i.e. for about half of the four-column groups.
+// This kernel
+//  (1) keeps TWO query tiles resident per CTA and streams train tiles of 128 rows through a 3-stage ring, so one 36 KB
+//      stage feeds two M = 128 MMAs (half the operand bytes per flop);
+//  (2) lets the tensor core produce the finished squared distance, offset into one binade: seven extra K columns carry
+//      |t|^2 and |q|^2 as base-256 digits against {1, 256, 256} and the constant 2^23 = 4096 * 2048, so the accumulator
+//      is  d + 2^23  with d = |q|^2 + |t|^2 - 2 q.t in [0, 128 * 255^2] -- an integer in [2^23, 2^24), whose float32 bit
+//      pattern is 0x4B000000 | d.  Every operand is an integer fp16 holds exactly and every partial sum an integer below
+//      2^24, so this is exact.  The 16 extra K columns travel as their own 32-byte-swizzled TMA boxes and cost one more
+//      UMMA_K step (K = 144);
+//  (3) scans WITHOUT a branch: key = bits * 64 + (0x80000000 | column) = 0x40000000 | d << 6 | column is a positive normal
+//      float pattern ordered like (d, column), so a min / max network of FMNMX / FMNMX3 on the keys gives the two smallest
+//      (distance, lowest column first) of the thread's 64 columns in ~220 independent instructions -- no update path, no
+//      shared bounds, no dependence on the data;
+//  (4) spreads (query pair, train tile) units over all SMs in contiguous runs (a run may cross into the next query pair:
+//      the A tiles are reloaded and the rows' partial top-2 go to the CTA's slot of that pair).
 #define K3_BN 128
 #define K3_STAGES 3
 #define K3_A_HALF (KNN_BM * KNN_DIM * 2 + KNN_BM * 32)        // 32 KB main + 4 KB extra columns
 #define K3_B_STAGE (K3_BN * KNN_DIM * 2 + K3_BN * 32)         // 32 KB + 4 KB
-#define K3_SMEM (1024 + 2 * K3_A_HALF + K3_STAGES * K3_B_STAGE + 256 + 2 * KNN_BM * 2 * 8)
+#define K3_SMEM (1024 + 2 * K3_A_HALF + K3_STAGES * K3_B_STAGE + 256)
 
 __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr)
 {
@@ -287,6 +294,21 @@ __device__ __forceinline__ void tc_ld_wait32(uint32_t* v)
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                  :: "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait16(uint32_t* v)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
     float d;
@@ -294,8 +316,10 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
     return d;
 }
 
-// f32 -> fp16 operands of the kernel below.  query: -2 q | {1, 256, 256, 0 ..}; train: t | {a0, a1, 256 a2, 0 ..}; rows
-// beyond n: zeros | {0, 0, 65504}: d' = 16 769 024 against any query, above every real d' (<= 128 * 255^2)
+// f32 -> fp16 operands of the kernel below.  Extra K columns (16 per row):
+//   query: -2 q | {1, 256, 256,  q0, q1, 256 q2,  4096, 0 ..}     train: t | {a0, a1, 256 a2,  1, 256, 256,  2048, 0 ..}
+// with |q|^2 = q0 + 256 q1 + 65536 q2 and |t|^2 = a0 + 256 a1 + 65536 a2: the extra columns contribute
+// |t|^2 + |q|^2 + 2^23.  Rows beyond n are zero vectors (their columns are masked in the scan / dropped in the merge).
 __global__ void __launch_bounds__(256)
 knn_prep3_kernel(const float* __restrict__ src, int n, int n_pad, int is_query, __half* __restrict__ dst, __half* __restrict__ ext,
                  float* __restrict__ norm, int* __restrict__ bad)
@@ -324,13 +348,13 @@ knn_prep3_kernel(const float* __restrict__ src, int n, int n_pad, int is_query, 
     if (!__all_sync(0xffffffffu, ok) && lane == 0) atomicOr(bad, 1);
     if (lane == 0 && norm) norm[row] = s;
     if (lane < 16) {
+        const int si = (ok && row < n) ? (int)s : 0;
+        const float dig = lane % 3 == 0 ? (float)(si & 255) : lane % 3 == 1 ? (float)((si >> 8) & 255) : (float)((si >> 16) * 256);
+        const float one = lane % 3 == 0 ? 1.f : 256.f;
         float e = 0.f;
-        if (is_query) e = lane == 0 ? 1.f : (lane < 3 ? 256.f : 0.f);
-        else if (row >= n) e = lane == 2 ? 65504.f : 0.f;
-        else {
-            const int si = ok ? (int)s : 0;
-            e = lane == 0 ? (float)(si & 255) : lane == 1 ? (float)((si >> 8) & 255) : lane == 2 ? (float)((si >> 16) * 256) : 0.f;
-        }
+        if (lane < 3) e = is_query ? one : dig;          // against the train row's |t|^2 digits
+        else if (lane < 6) e = is_query ? dig : one;     // the query row's |q|^2 digits
+        else if (lane == 6) e = is_query ? 4096.f : 2048.f;
         ext[(size_t)row * 16 + lane] = __float2half_rn(e);
     }
 }
@@ -338,9 +362,10 @@ knn_prep3_kernel(const float* __restrict__ src, int n, int n_pad, int is_query, 
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_gemm_top2_m256_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qx,
                           const __grid_constant__ CUtensorMap map_t, const __grid_constant__ CUtensorMap map_tx,
-                          const float* __restrict__ qnorm, int n_tiles, int per, int total, KnnPartial* __restrict__ partial, int nq_pad,
-                          int* __restrict__ gbound)
+                          int n_tiles, int per, int total, int nt, KnnPartial* __restrict__ partial, int nq_pad, int dbg)
 {
+    // dbg (benchmarks only, B200VO_KNN_DBG): 1 = the epilogue pulls the accumulators but does not reduce them (TMEM-read
+    // floor), 2 = it hands every accumulator stage straight back (TMA + MMA floor); results are meaningless then
     extern __shared__ uint8_t smem_raw[];
     const int f0 = blockIdx.x * per, f1 = min(f0 + per, total);
     if (f0 >= f1) return;                      // uniform: before any barrier / TMEM allocation
@@ -349,25 +374,23 @@ knn_gemm_top2_m256_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     const uint32_t sB = base + 2 * K3_A_HALF;
     const uint32_t sBar = sB + K3_STAGES * K3_B_STAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + (sBar + 128 - smem_u32(smem_raw)));
-    // [256 rows][2 column groups] {running second-best, segment tag} as one 64-bit word each
-    volatile unsigned long long* tau_v = reinterpret_cast<volatile unsigned long long*>(smem_raw + (sBar + 256 - smem_u32(smem_raw)));
+    // accumulator barriers per (TMEM stage, query half): the eight epilogue warps of a half start on its 128 columns while
+    // the MMAs of the other half are still running
     const uint32_t bar_a = sBar, bar_aempty = sBar + 8, bar_bfull = sBar + 16, bar_bempty = sBar + 40, bar_accfull = sBar + 64,
-                   bar_accempty = sBar + 80;
+                   bar_accempty = sBar + 96;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_a, 1);
         mbar_init(bar_aempty, 1);
         for (int s = 0; s < K3_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, 32 * KNN_EPI_WARPS); }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, 32 * KNN_EPI_WARPS / 2); }
         mbar_fence_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // shared bounds start as "tag = no segment" (shared memory keeps what the previous CTA on this SM left there)
-    if (threadIdx.x < 2 * KNN_BM * 2) tau_v[threadIdx.x] = 0xFFFFFFFF00000000ull;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -411,12 +434,12 @@ knn_gemm_top2_m256_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
                 for (int n = na; n < nb; ++n, ++it) {
                     const int s = it % K3_STAGES, ph = (it / K3_STAGES) & 1;
                     const int as = it & 1, aph = (it >> 1) & 1;
-                    mbar_wait(bar_accempty + 8 * as, aph ^ 1);
                     mbar_wait(bar_bfull + 8 * s, ph);
-                    tc_fence_after();
                     const uint32_t sBs = sB + s * K3_B_STAGE;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        mbar_wait(bar_accempty + 8 * (as * 2 + h), aph ^ 1);
+                        tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + h * 128);
                         const uint32_t sAh = sA + h * K3_A_HALF;
 #pragma unroll
@@ -428,9 +451,9 @@ knn_gemm_top2_m256_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
                                 tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                         }
                         tc_mma_f16(d_tmem, umma_desc_sw32(sAh + KNN_BM * 256), umma_desc_sw32(sBs + K3_BN * 256), idesc, 1);   // the norm columns
+                        if (h == 1) tc_commit(bar_bempty + 8 * s);              // smem stage free once these MMAs have read it
+                        tc_commit(bar_accfull + 8 * (as * 2 + h));              // this half's accumulator is ready for the epilogue
                     }
-                    tc_commit(bar_bempty + 8 * s);      // smem stage free once these MMAs have read it
-                    tc_commit(bar_accfull + 8 * as);    // accumulators ready for the epilogue
                 }
                 tc_commit(bar_aempty);                  // every MMA of this segment has read the A tiles
                 f += nb - na;
@@ -438,106 +461,118 @@ knn_gemm_top2_m256_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         }
     } else {
         // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31.  Sixteen warps = 4 lane quadrants x 2 query halves x 2
-        // column groups of 64; one query row per thread.  The accumulator already holds d' = |t|^2 - 2 q.t (|q|^2 is
-        // constant per row and added at the end); exact integers in fp32.
+        // column groups of 64; one query row per thread.  The accumulator holds d + 2^23 (see above).
         const int q = warp & 3;
         const int idx = (warp - 2) >> 2;
         const int h = idx >> 1, cg = idx & 1;
         const int rl = h * KNN_BM + q * 32 + lane;          // row inside the query pair
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 128 + cg * 64);
-        int it = 0, seg = 0;
-        uint32_t va[32], vb[32];
-        {   // first piece of the first unit; from here on the pieces form one software pipeline across units and segments:
-            // while a piece is scanned the next one's tcgen05.ld is in flight
-            mbar_wait(bar_accfull, 0);
+        const int pad_tile = (nt % K3_BN) ? n_tiles - 1 : -1;   // the train tile that holds rows beyond nt
+        int it = 0;
+        uint32_t va[16], vb[16];
+        if (dbg == 2) {
+            for (int i = 0; i < f1 - f0; ++i) {
+                mbar_wait(bar_accfull + 8 * ((i & 1) * 2 + h), (i >> 1) & 1);
+                tc_fence_after();
+                tc_fence_before();
+                mbar_arrive(bar_accempty + 8 * ((i & 1) * 2 + h));
+            }
+        } else {
+        {   // first 16-column piece of the first unit; from here on the pieces form one software pipeline across units and
+            // segments: while a piece is reduced the next one's tcgen05.ld is in flight
+            mbar_wait(bar_accfull + 8 * h, 0);
             tc_fence_after();
-            tc_ld32(lane_base, va);
+            tc_ld16(lane_base, va);
         }
-        for (int f = f0; f < f1; ++seg) {
+        for (int f = f0; f < f1;) {
             const int m = f / n_tiles, na = f - m * n_tiles, nb = min(n_tiles, na + (f1 - f));
             const int row = m * 2 * KNN_BM + rl;
-            float b1 = KNN_BIG, b2 = KNN_BIG;
-            int i1 = -1, i2 = -1;
-            tau_v[rl * 2 + cg] = 0xFFFFFFFF00000000ull;     // nothing to share yet in this segment (tag in the high word)
-            // Every CTA (and warp) that scans other train tiles for this query row publishes its running second-best -- as
-            // the true squared distance, a non-negative float whose bit pattern orders like an int -- in gbound[row].
-            // With a bound from the whole row (4-5 CTAs x 2 warps share a query pair at 8192 x 8192) the update path,
-            // which a warp enters when ANY of its 32 rows is displaced, runs for ~13 % of the groups instead of ~55 %.
-            // Pruning never removes a top-2 entry (the bound is some subset's second-best + 1), so the result does not
-            // depend on who publishes when.
-            const float qn = qnorm[row];
-            float published = KNN_BIG;
-            int gb = 0x7F7F7F7F, gb_next;
+            // running two smallest of this row over the segment's train tiles: (distance, train index), earlier tiles win ties
+            int r1d = 0x7FFFFFFF, r2d = 0x7FFFFFFF, r1i = -1, r2i = -1;
             for (int n = na; n < nb; ++n, ++it) {
                 const int as = it & 1;
                 const int j0 = n * K3_BN + cg * 64;
-                // the row's global bound is read one stage ahead (an L2 round trip): a bound that is one stage old is only weaker
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(gb_next) : "l"(gbound + row));
-                {   // the two warps of a row share their running second-best: anything strictly above the smaller of them
-                    // cannot enter the global top-2 (entries lowered this way carry index -1)
-                    const unsigned long long e = tau_v[rl * 2 + (cg ^ 1)];
-                    float tau = KNN_BIG;
-                    if ((uint32_t)(e >> 32) == (uint32_t)seg) tau = __uint_as_float((uint32_t)e);
-                    tau = fminf(tau, __fsub_rn(__int_as_float(gb), qn)) + 1.0f;      // exact integers (or huge); next value up
-                    if (tau < b2) { b2 = tau; i2 = -1; }
-                }
-                tc_ld_wait32(va);
-                tc_ld32(lane_base + (uint32_t)(as * 256 + 32), vb);          // in flight while the first piece is scanned
+                float s1[4], s2[4];     // the two smallest keys of each 16-column piece
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t* v = c ? vb : va;
-                    if (c == 1) {
-                        tc_ld_wait32(vb);
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t* v = (c & 1) ? vb : va;
+                    tc_ld_wait16(v);
+                    if (c < 3) {
+                        tc_ld16(lane_base + (uint32_t)(as * 256 + (c + 1) * 16), (c & 1) ? va : vb);   // in flight while this piece is reduced
+                    } else {
                         tc_fence_before();
-                        mbar_arrive(bar_accempty + 8 * as);                   // both pieces are in registers
-                        if (f + (n - na) + 1 < f1) {                          // first piece of the next unit (this or the next segment)
-                            const int it2 = it + 1;
-                            mbar_wait(bar_accfull + 8 * (it2 & 1), (it2 >> 1) & 1);
-                            tc_fence_after();
-                            tc_ld32(lane_base + (uint32_t)((it2 & 1) * 256), va);
+                        mbar_arrive(bar_accempty + 8 * (as * 2 + h));                 // all four pieces are in registers
+                    }
+                    // key = bits * 64 + (0x80000000 | column) = 0x40000000 | d << 6 | column: positive normal float patterns
+                    // ordered like (d, column)
+                    float k[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) k[e] = __uint_as_float(v[e] * 64u + (0x80000000u | (uint32_t)(c * 16 + e)));
+                    if (dbg == 1) {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) x ^= v[e];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) k[e] = __uint_as_float(0x7F000000u | (x & 1u));      // keeps the loads alive, skips the network below
+                    }
+                    if (c == 3 && f + (n - na) + 1 < f1) {                            // first piece of the next unit (vb's keys are built, va is free)
+                        const int it2 = it + 1;
+                        mbar_wait(bar_accfull + 8 * ((it2 & 1) * 2 + h), (it2 >> 1) & 1);
+                        tc_fence_after();
+                        tc_ld16(lane_base + (uint32_t)((it2 & 1) * 256), va);
+                    }
+                    if (n == pad_tile) {      // rows beyond nt: never candidates
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) k[e] = (j0 + c * 16 + e) < nt ? k[e] : __uint_as_float(0x7F000000u);
+                    }
+                    // two smallest of 16 distinct keys: sorted pairs, then merges (a1 <= a2) + (b1 <= b2) ->
+                    // (min(a1, b1), min(max(a1, b1), a2, b2))
+                    float lo[8], hi[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { lo[e] = fminf(k[2 * e], k[2 * e + 1]); hi[e] = fmaxf(k[2 * e], k[2 * e + 1]); }
+#pragma unroll
+                    for (int w = 4; w >= 1; w >>= 1) {
+#pragma unroll
+                        for (int e = 0; e < w; ++e) {
+                            const float a1 = lo[e], b1 = lo[e + w];
+                            lo[e] = fminf(a1, b1);
+                            hi[e] = fmin3(fmaxf(a1, b1), hi[e], hi[e + w]);
                         }
                     }
-                    const int jc = j0 + c * 32;
+                    s1[c] = lo[0]; s2[c] = hi[0];
+                }
+                // the four pieces' pairs -> the stage's two smallest (keys order ties by column)
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float d0 = __uint_as_float(v[g * 4 + 0]), d1 = __uint_as_float(v[g * 4 + 1]);
-                        const float d2 = __uint_as_float(v[g * 4 + 2]), d3 = __uint_as_float(v[g * 4 + 3]);
-                        const float mn = fminf(fmin3(d0, d1, d2), d3);
-                        if (mn < b2) {   // some lane's running second-best is displaced inside this group of four
-                            const float dd[4] = {d0, d1, d2, d3};
+                for (int w = 2; w >= 1; w >>= 1) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float d = dd[e];
-                                if (d < b2) {
-                                    const int j = jc + g * 4 + e;
-                                    const bool lt1 = d < b1;           // strict: ascending j, the lower train index wins ties
-                                    i2 = lt1 ? i1 : j;
-                                    b2 = lt1 ? b1 : d;
-                                    i1 = lt1 ? j : i1;
-                                    b1 = lt1 ? d : b1;
-                                }
-                            }
-                        }
+                    for (int e = 0; e < w; ++e) {
+                        const float a1 = s1[e], b1 = s1[e + w];
+                        s1[e] = fminf(a1, b1);
+                        s2[e] = fmin3(fmaxf(a1, b1), s2[e], s2[e + w]);
                     }
                 }
-                gb = gb_next;
-                tau_v[rl * 2 + cg] = ((unsigned long long)(uint32_t)seg << 32) | __float_as_uint(b2);
-                {   // a lowered bound (index -1) is some second-best + 1: publish the second-best itself
-                    const float mine = i2 >= 0 ? b2 : b2 - 1.0f;
-                    if (mine < published) {
-                        published = mine;
-                        atomicMin(gbound + row, __float_as_int(__fadd_rn(mine, qn)));
-                    }
-                }
+                const float t1 = s1[0], t2 = s2[0];
+                const uint32_t u1 = __float_as_uint(t1), u2 = __float_as_uint(t2);
+                const int n1d = (int)((u1 >> 6) & 0x7FFFFFu), n2d = (int)((u2 >> 6) & 0x7FFFFFu);
+                const int n1i = u1 >= 0x7F000000u ? -1 : j0 + (int)(u1 & 63u), n2i = u2 >= 0x7F000000u ? -1 : j0 + (int)(u2 & 63u);
+                const int m1d = n1i < 0 ? 0x7FFFFFFF : n1d, m2d = n2i < 0 ? 0x7FFFFFFF : n2d;
+                // merge into the running pair; on equal distance the running entry (a lower train index) stays ahead
+                const bool first = m1d < r1d;
+                const int o2d = first ? (r1d <= m2d ? r1d : m2d) : (m1d < r2d ? m1d : r2d);
+                const int o2i = first ? (r1d <= m2d ? r1i : n2i) : (m1d < r2d ? n1i : r2i);
+                r1i = first ? n1i : r1i;
+                r1d = first ? m1d : r1d;
+                r2d = o2d; r2i = o2i;
             }
             KnnPartial p;
-            p.d1 = i1 >= 0 ? __fadd_rn(b1, qn) : KNN_BIG;
-            p.d2 = i2 >= 0 ? __fadd_rn(b2, qn) : KNN_BIG;
-            p.i1 = i1; p.i2 = i2;
+            p.d1 = r1i >= 0 ? (float)r1d : KNN_BIG;
+            p.d2 = r2i >= 0 ? (float)r2d : KNN_BIG;
+            p.i1 = r1i; p.i2 = r2i;
             const int slot = (int)blockIdx.x - (m * n_tiles) / per;       // this CTA's position among those sharing query pair m
             partial[((size_t)slot * 2 + cg) * nq_pad + row] = p;
             f += nb - na;
         }
+        }   // dbg != 2
     }
     tc_fence_before();
     __syncthreads();
@@ -658,24 +693,19 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
     const int n_splits = (n_tiles + per - 1) / per + 1;      // CTAs that can share one query pair
     const size_t b_q16 = vo_align((size_t)nq_pad * KNN_DIM * 2, 1024), b_t16 = vo_align((size_t)nt_pad * KNN_DIM * 2, 1024);
     const size_t b_qx = vo_align((size_t)nq_pad * 32, 1024), b_tx = vo_align((size_t)nt_pad * 32, 1024);
-    const size_t b_qn = vo_align((size_t)nq_pad * 4, 256);
     const size_t b_part = vo_align((size_t)2 * n_splits * nq_pad * sizeof(KnnPartial), 256);
-    const size_t b_gb = vo_align((size_t)nq_pad * 4, 256);
-    VO_TRY(vo_reserve(ctx, ctx->d_scratch[3], b_q16 + b_t16 + b_qx + b_tx + b_qn + b_part + b_gb + 256));
+    VO_TRY(vo_reserve(ctx, ctx->d_scratch[3], b_q16 + b_t16 + b_qx + b_tx + b_part + 256));
     uint8_t* d = (uint8_t*)ctx->d_scratch[3].p;
     __half* q16 = (__half*)d; d += b_q16;
     __half* t16 = (__half*)d; d += b_t16;
     __half* qx = (__half*)d; d += b_qx;
     __half* tx = (__half*)d; d += b_tx;
-    float* qn = (float*)d; d += b_qn;
     KnnPartial* part = (KnnPartial*)d; d += b_part;
-    int* gbound = (int*)d; d += b_gb;
     int* bad = (int*)d;
     ctx->knn_bad_flag = bad;
     VO_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
     VO_CUDA(ctx, cudaMemsetAsync(part, 0xFF, b_part, ctx->stream));   // lists no CTA writes: index -1 = "no entry"
-    VO_CUDA(ctx, cudaMemsetAsync(gbound, 0x7F, b_gb, ctx->stream));   // 0x7F7F7F7F = 3.4e38: no bound yet
-    knn_prep3_kernel<<<(nq_pad + 7) / 8, 256, 0, ctx->stream>>>(q_dev, nq, nq_pad, 1, q16, qx, qn, bad);
+    knn_prep3_kernel<<<(nq_pad + 7) / 8, 256, 0, ctx->stream>>>(q_dev, nq, nq_pad, 1, q16, qx, nullptr, bad);
     knn_prep3_kernel<<<(nt_pad + 7) / 8, 256, 0, ctx->stream>>>(t_dev, nt, nt_pad, 0, t16, tx, nullptr, bad);
     ctx->launches += 2;
     CUtensorMap map_q, map_t, map_qx, map_tx;
@@ -688,8 +718,9 @@ int vo_knn2_ratio_dev(b200vo_ctx* ctx, const float* q_dev, int nq, const float* 
         VO_CUDA(ctx, cudaFuncSetAttribute(knn_gemm_top2_m256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM));
         attr_done = true;
     }
-    knn_gemm_top2_m256_kernel<<<(total + per - 1) / per, KNN_THREADS, K3_SMEM, ctx->stream>>>(map_q, map_qx, map_t, map_tx, qn, n_tiles, per, total,
-                                                                                               part, nq_pad, gbound);
+    static const int dbg = getenv("B200VO_KNN_DBG") ? atoi(getenv("B200VO_KNN_DBG")) : 0;
+    knn_gemm_top2_m256_kernel<<<(total + per - 1) / per, KNN_THREADS, K3_SMEM, ctx->stream>>>(map_q, map_qx, map_t, map_tx, n_tiles, per, total, nt,
+                                                                                               part, nq_pad, dbg);
     knn_finalize_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(part, 2 * n_splits, nq, nq_pad, nt, ratio, idx2_dev, dist2_dev, accept_dev);
     ctx->launches += 2;
     VO_CUDA(ctx, cudaGetLastError());
