@@ -8,7 +8,11 @@ sizes, maxLevel 0..6, all three criteria types, points on quarter-pixel grids an
 211 goodFeaturesToTrack, 210 knnMatch (with planted duplicate descriptors), 210 solvePnPRansac,
 210 findEssentialMat + recoverPose, 210 min-distance masks: 0 mismatches.  Seeds 2 and 3 (500 s, + 428
 triangulation loops): one findEssentialMat mask differing in ONE point (threshold tie, see below), nothing else.
-Seed 4 (330 s, 3 372 calls) and seed 6 on the final round-1 binary (300 s, 3 012 calls): 0 mismatches."""
+Seed 4 (330 s, 3 372 calls) and seed 6 on the final round-1 binary (300 s, 3 012 calls): 0 mismatches.
+Round 2 (SIFT added; persistent tracker, fused pose kernel, second kNN kernel): seed 11 (180 s) one findEssentialMat case with
+4 mask points -- an ill-conditioned sample on which cv2 sides with the CUDA path (the oracle's
+root termination was aligned afterwards); seeds 21 and 22 on the round's final binary (240 s each, 1 700 + 1 800 calls incl.
+303 SIFT frames of random sizes): 0 mismatches."""
 import os
 import sys
 import time
