@@ -158,12 +158,16 @@ klt_kernel_v3(const KltArgs a)
     const float eps_lo = a.eps_lo, eps_hi = a.eps_hi;
 
     // ---- work queue: a.queue[0] = next feature slot, a.queue[1] = warps that found the queue empty ----
+    // The next slot is fetched one feature ahead (the atomic's round trip hides behind the feature) only when the launch
+    // has at least two features per warp: in a small launch (a single sequence: 1000 features for 1000 warps) fetching
+    // ahead lets the first half of the warps claim two features each while the other half of the machine gets none.
+    const bool ahead = total >= 2 * (int)gridDim.x * KLT_WARPS;
     int gw = 0;
     if (lane == 0) gw = atomicAdd(a.queue, 1);
     gw = __shfl_sync(0xffffffffu, gw, 0);
     while (gw < total) {
         int gw_next = 0;
-        if (lane == 0) gw_next = atomicAdd(a.queue, 1);   // fetched now, consumed when this feature is done
+        if (ahead && lane == 0) gw_next = atomicAdd(a.queue, 1);   // fetched now, consumed when this feature is done
         const int seq = gw / cap_all;
         int pi = gw - seq * cap_all;
         const int seg = pi >= a.cap[0] ? 1 : 0;
@@ -469,6 +473,7 @@ klt_kernel_v3(const KltArgs a)
         if (a.err[seg]) a.err[seg][pidx] = e;
     }
         }   // pi < n_here
+        if (!ahead && lane == 0) gw_next = atomicAdd(a.queue, 1);
         gw = __shfl_sync(0xffffffffu, gw_next, 0);
     }
     // the last warp of the grid to find the queue empty re-arms it for the next launch that uses this slot
