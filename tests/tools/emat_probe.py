@@ -1,10 +1,10 @@
 """Finds and dissects a findEssentialMat case where the CUDA mask and the oracle's differ (fuzz record: n = 1002,
 outlier fraction 0.12188663426661836, 4 points): which sample / model the two loops choose and how the per-model
-inlier counts compare on the SAME sample set.  python benchmarks/emat_probe.py [n of [seed]]"""
+inlier counts compare on the SAME sample set.  python tests/tools/emat_probe.py [n of [seed]]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import numpy as np  # noqa: E402

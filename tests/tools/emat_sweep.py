@@ -1,9 +1,9 @@
 """Three-way sweep of findEssentialMat: CUDA path vs the C oracle vs cv2 on random synthetic pairs.
-python benchmarks/emat_sweep.py [cases]"""
+python tests/tools/emat_sweep.py [cases]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import numpy as np  # noqa: E402
