@@ -11,8 +11,8 @@ triangulation loops): one findEssentialMat mask differing in ONE point (threshol
 Seed 4 (330 s, 3 372 calls) and seed 6 on the final round-1 binary (300 s, 3 012 calls): 0 mismatches.
 Round 2 (SIFT added; persistent tracker, fused pose kernel, second kNN kernel): seed 11 (180 s) one findEssentialMat case with
 4 mask points -- an ill-conditioned sample on which cv2 sides with the CUDA path (the oracle's
-root termination was aligned afterwards); seeds 21 and 22 on the round's final binary (240 s each, 1 700 + 1 800 calls incl.
-303 SIFT frames of random sizes): 0 mismatches."""
+root termination was aligned afterwards); seeds 21 and 22 (240 s each, 1 700 + 1 800 calls incl. 303 SIFT frames of random
+sizes) and, after the last kernel changes (branch-free kNN scan, tracker queue fix), seeds 31 and 32 (3 450 calls): 0 mismatches."""
 import os
 import sys
 import time
