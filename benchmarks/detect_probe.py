@@ -1,7 +1,6 @@
 """Batched Shi-Tomasi detection on 64 resident KITTI-shaped frames: wall time per call (for ncu launch lists)."""
 import sys, time
 sys.path.insert(0, '.')
-import numpy as np
 from monocular_visual_odometry_va4mr_b200 import workload
 from monocular_visual_odometry_va4mr_b200.batch import SequenceBatch
 wl = workload.TrackWorkload("kitti", batch=64, n_frames=2, n_landmarks=100, n_candidates=100, n_distinct=2, seed=0, cap_landmarks=128, cap_candidates=128)

@@ -18,7 +18,7 @@ NAMES = ["compaction", "ransac chunks (subsets + 32 P3P + scoring + replay)", "w
 
 def main():
     import torch
-    from monocular_visual_odometry_va4mr_b200 import _lib, workload
+    from monocular_visual_odometry_va4mr_b200 import _lib
     args = bench.parse(["--batch", "1", "--distinct", "1"])
     wl = bench.make_workload(args, 1, 0)
     ctx = _lib.Context(0)
