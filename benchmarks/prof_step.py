@@ -30,7 +30,7 @@ def main():
     ctx = _lib.Context(0)
     wl = bench.make_workload(args, a.batch, 0)
     arm = bench.Arm(args, opts, ctx, wl, 1, 0, a.batch)
-    res = arm.device_resident([a.batch])
+    res = arm.device_resident([a.batch])   # timed loop without the profiler, stage times from the pass behind it
     n = max(res["nprof"], 1)
     print(f"prof_step: batch {a.batch}: {res['dev_ms'] / arm.K:.4f} ms/step, {a.batch * arm.K / (res['dev_ms'] * 1e-3):.0f} frames/s, "
           f"stages (ms) pyramid {res['stage_ms'][0] / n:.4f} klt_landmarks {res['stage_ms'][1] / n:.4f} pose|cand {res['stage_ms'][2] / n:.4f}, "

@@ -5,6 +5,7 @@
 // sequence of the batch, the previous frame's pyramid stays resident in HBM between steps, and
 // nothing returns to the host between KLT and PnP.
 #include "internal.cuh"
+#include <chrono>
 #include "pnp.cuh"
 
 #define B200VO_BATCH_CHUNKS 4
@@ -36,6 +37,13 @@ struct b200vo_batch {
     DevBuf outs;             // host-input path: outputs
     DevBuf work;             // compacted landmarks + PnP workspace
     DevBuf gftt_ws;          // batched corner detection workspace
+    DevBuf stamps;           // B200VO_TRACE_FILE: GPU wall clock at points of the host-buffer step's streams ([64 steps][4])
+    long stamp_step = 0;
+    DevBuf trace;            // B200VO_TRACE_FILE: wall-clock stamps of the pose CTAs of the last step ([batch][16] int64)
+    double host_us[6] = {};  // B200VO_TRACE_FILE: host time inside b200vo_batch_step, summed: entry->inputs enqueued->kernels enqueued->
+    long host_n = 0;         //                    read-back enqueued->synchronised->return, and between two calls
+    double host_last_exit = 0;
+    long host_calls = 0;
     // carved from `work`
     float* c_obj; float* c_img; int* c_n; int* c_orig; int* inliers; uint8_t* c_mask;
     void* pnp_ws;
@@ -51,7 +59,7 @@ struct b200vo_batch {
     // high-priority stream beside the candidate tracker (which fills the SMs) instead of after it
     cudaStream_t pose_stream = nullptr;
     cudaEvent_t lm_ev = nullptr, cand_ev = nullptr, pose_ev = nullptr;
-    cudaEvent_t obj_ev = nullptr, klt_ev = nullptr, io_ev = nullptr;
+    cudaEvent_t obj_ev = nullptr, klt_ev = nullptr, io_ev = nullptr, cand_in_ev = nullptr;
     // optional per-kernel timing (CUDA events on the ctx stream): [step][stage] boundaries
     bool profile = false;
     int prof_n = 0;
@@ -165,7 +173,7 @@ extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batc
         for (auto& e : B->copy_ev) ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&B->done_ev, cudaEventDisableTiming));
         ok(cudaStreamCreateWithFlags(&B->io_stream, cudaStreamNonBlocking));
-        for (cudaEvent_t* e : {&B->obj_ev, &B->klt_ev, &B->io_ev, &B->lm_ev, &B->cand_ev, &B->pose_ev})
+        for (cudaEvent_t* e : {&B->obj_ev, &B->klt_ev, &B->io_ev, &B->lm_ev, &B->cand_ev, &B->pose_ev, &B->cand_in_ev})
             ok(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         ok(cudaStreamCreateWithPriority(&B->pose_stream, cudaStreamNonBlocking, greatest));
         for (auto& e : B->q_ev) ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -187,11 +195,61 @@ extern "C" int b200vo_batch_create(b200vo_ctx* ctx, int batch, const b200vo_batc
     return 0;
 }
 
+__global__ void trace_stamp_kernel(unsigned long long* dst)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    *dst = t;
+}
+
+// B200VO_TRACE_FILE=<path>: when the batch is destroyed, write where and when (GPU wall clock, ns) the pose CTAs of the LAST
+// step ran and when the most recent tracker launches claimed their first feature / retired their last warp -- the
+// picture of how the pose chain and the candidate tracker share the machine that CUDA events cannot give.
+static void batch_write_trace(b200vo_batch* B)
+{
+    const char* path = getenv("B200VO_TRACE_FILE");
+    if (!path || !B->trace.p) return;
+    cudaDeviceSynchronize();
+    std::vector<long long> t((size_t)B->batch * 16);
+    if (cudaMemcpy(t.data(), B->trace.p, t.size() * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    std::vector<unsigned long long> q;
+    vo_klt_trace_read(B->ctx, q);
+    FILE* f = fopen(path, "w");
+    if (!f) return;
+    long long t0 = 0;
+    for (int b = 0; b < B->batch; ++b) if (!t0 || (t[(size_t)b * 16 + 12] && t[(size_t)b * 16 + 12] < t0)) t0 = t[(size_t)b * 16 + 12];
+    fprintf(f, "# pose CTAs of the last step: sequence, SM, start and end in us after the first pose CTA started\n");
+    for (int b = 0; b < B->batch; ++b)
+        fprintf(f, "pose %d sm %lld start %.1f end %.1f\n", b, t[(size_t)b * 16 + 13], (t[(size_t)b * 16 + 12] - t0) * 1e-3,
+                (t[(size_t)b * 16 + 14] - t0) * 1e-3);
+    if (B->host_n)
+        fprintf(f, "# host side of b200vo_batch_step, mean us over %ld calls: inputs enqueued %.1f, kernels enqueued %.1f, read-back enqueued %.1f, "
+                   "synchronised %.1f, returned %.1f; between calls %.1f\n", B->host_n, B->host_us[0] / B->host_n, B->host_us[1] / B->host_n,
+                B->host_us[2] / B->host_n, B->host_us[3] / B->host_n, B->host_us[4] / B->host_n, B->host_us[5] / B->host_n);
+    if (B->stamps.p) {
+        std::vector<unsigned long long> st(64 * 4);
+        if (cudaMemcpy(st.data(), B->stamps.p, st.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            fprintf(f, "# host-buffer steps, same clock: point arrays uploaded (first kernel may start), results read back (the call returns)\n");
+            for (long k = B->stamp_step > 24 ? B->stamp_step - 24 : 0; k < B->stamp_step; ++k)
+                fprintf(f, "step %ld uploaded %.1f read_back %.1f (candidate results: from %.1f to %.1f)\n", k, ((long long)st[(k & 63) * 4] - t0) * 1e-3,
+                        ((long long)st[(k & 63) * 4 + 1] - t0) * 1e-3, ((long long)st[(k & 63) * 4 + 2] - t0) * 1e-3, ((long long)st[(k & 63) * 4 + 3] - t0) * 1e-3);
+        }
+    }
+    fprintf(f, "# tracker launches (queue ring), same clock: first feature claimed, last warp retired\n");
+    for (size_t i = 0; i + 1 < q.size(); i += 2)
+        if (q[i] && (long long)q[i + 1] > t0 - 60000000)
+            fprintf(f, "klt slot %d start %.1f end %.1f\n", (int)(i / 2), ((long long)q[i] - t0) * 1e-3, ((long long)q[i + 1] - t0) * 1e-3);
+    fclose(f);
+}
+
 extern "C" void b200vo_batch_destroy(b200vo_batch* B)
 {
     if (!B) return;
     cudaSetDevice(B->ctx->device);
     cudaStreamSynchronize(B->ctx->stream);
+    batch_write_trace(B);
+    if (B->trace.p) cudaFree(B->trace.p);
+    if (B->stamps.p) cudaFree(B->stamps.p);
     auto kill_stream = [](cudaStream_t st) { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } };
     auto kill_event = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
     kill_stream(B->pre_stream);
@@ -203,7 +261,7 @@ extern "C" void b200vo_batch_destroy(b200vo_batch* B)
     for (auto& e : B->q_ev) kill_event(e);
     for (auto& e : B->chunk_ev) kill_event(e);
     for (auto& e : B->copy_ev) kill_event(e);
-    for (cudaEvent_t e : {B->step_end_ev, B->done_ev, B->obj_ev, B->klt_ev, B->io_ev, B->lm_ev, B->cand_ev, B->pose_ev}) kill_event(e);
+    for (cudaEvent_t e : {B->step_end_ev, B->done_ev, B->obj_ev, B->klt_ev, B->io_ev, B->lm_ev, B->cand_ev, B->pose_ev, B->cand_in_ev}) kill_event(e);
     if (B->prof_init) for (auto& row : B->prof_ev) for (auto& e : row) kill_event(e);
     cudaGetLastError();
     delete B;
@@ -374,6 +432,11 @@ static int batch_pose(b200vo_batch* B, const float* lm_obj, const int* n_lm, con
     a.inliers = B->inliers; a.mask = B->c_mask; a.pose = pose;
     vo_pnp_carve_workspace(a, B->pnp_ws);
     a.ok = a.ok_ws;
+    static const char* trace_file = getenv("B200VO_TRACE_FILE");   // measurement aid, see batch_write_trace
+    if (trace_file) {
+        VO_TRY(vo_reserve(ctx, B->trace, (size_t)B->batch * 16 * sizeof(long long)));
+        a.phase_clk = (long long*)B->trace.p;
+    }
     if (vo_pnp_fused_ok(a, true)) {
         // compaction, RANSAC, EPnP and the mask over the original slots: one CTA per sequence, one launch
         PoseBatchIO io;
@@ -412,7 +475,8 @@ static int batch_finish(b200vo_batch* B)
 static int batch_track_pose_overlapped(b200vo_batch* B, const uint8_t* frames_dev, const float* lm_pts, const float* lm_obj,
                                        const int* n_lm, const float* cand_pts, const int* n_cand, float* lm_next,
                                        uint8_t* lm_status, float* cand_next, uint8_t* cand_status, double* pose,
-                                       uint8_t* pnp_ok, uint8_t* inlier_mask, int* n_inliers, cudaEvent_t obj_ready)
+                                       uint8_t* pnp_ok, uint8_t* inlier_mask, int* n_inliers, cudaEvent_t obj_ready,
+                                       cudaEvent_t cand_ready = nullptr)
 {
     b200vo_ctx* ctx = B->ctx;
     cudaStream_t main_stream = ctx->stream;
@@ -430,7 +494,9 @@ static int batch_track_pose_overlapped(b200vo_batch* B, const uint8_t* frames_de
     // The tracker is a persistent kernel (one grid fills every SM until its queue is empty): launched beside the
     // landmark set, the candidate set would hold half the machine and the landmark tracks -- which the pose chain
     // waits for -- would take twice as long.  So: landmark set alone, then candidate set and pose chain side by side.
-    VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->lm_ev, 0));
+    static const bool serial = getenv("B200VO_POSE_SERIAL") != nullptr;   // A/B switch for measurements: candidate set after the pose chain
+    VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, serial ? B->pose_ev : B->lm_ev, 0));
+    if (cand_ready) VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, cand_ready, 0));   // candidate keypoints uploaded beside the landmark tracker
     VO_TRY(batch_track(B, 0, B->batch, frames_dev, lm_pts, n_lm, cand_pts, n_cand, lm_next, lm_status, cand_next, cand_status, 2));
     VO_CUDA(ctx, cudaEventRecord(B->cand_ev, main_stream));
     VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->pose_ev, 0));
@@ -490,14 +556,18 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
         return B200VO_E_BADARG;
     b200vo_ctx* ctx = B->ctx;
     const b200vo_batch_cfg& c = B->cfg;
+    static const bool host_trace = getenv("B200VO_TRACE_FILE") != nullptr;
+    auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double h_entry = host_trace ? now_us() : 0;
+    double h_in = 0, h_kern = 0, h_rb = 0, h_sync = 0;
     VO_CUDA(ctx, cudaSetDevice(ctx->device));
     VO_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     const int nb = B->batch, L = c.max_landmarks, Cn = c.max_candidates;
     const size_t fb = (size_t)c.rows * c.cols, f_total = fb * nb;
     // ---- inputs: frames (direct DMA when the caller's buffer is pinned) + one packed small block ----
     const size_t o_lmp = 0, o_lmo = o_lmp + vo_align((size_t)nb * L * 8, 256), o_nlm = o_lmo + vo_align((size_t)nb * L * 12, 256);
-    const size_t o_cp = o_nlm + vo_align((size_t)nb * 4, 256), o_nc = o_cp + vo_align((size_t)nb * Cn * 8, 256);
-    const size_t in_bytes = o_nc + vo_align((size_t)nb * 4, 256);
+    const size_t o_nc = o_nlm + vo_align((size_t)nb * 4, 256), o_cp = o_nc + vo_align((size_t)nb * 4, 256);   // the two count arrays are adjacent: one DMA
+    const size_t in_bytes = o_cp + vo_align((size_t)nb * Cn * 8, 256);
     // ---- outputs packed ----
     const size_t q_lmn = 0, q_lms = q_lmn + vo_align((size_t)nb * L * 8, 256), q_cn = q_lms + vo_align((size_t)nb * L, 256);
     const size_t q_cs = q_cn + vo_align((size_t)nb * Cn * 8, 256), q_pose = q_cs + vo_align((size_t)nb * Cn, 256);
@@ -563,6 +633,7 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     // cost more than the kernels between them.  Pack: one host memcpy per array into the staging block, ONE upload;
     // ONE read-back of the packed result block, host memcpy out.  Large batches keep the in-place DMA of every array.
     const bool packed = in_bytes + out_bytes <= (size_t)B200VO_PACKED_IO_BYTES;
+    bool cand_late = false;
     if (packed) {
         memcpy(hp + o_lmp, lm_pts, (size_t)nb * L * 8);
         memcpy(hp + o_lmo, lm_obj, (size_t)nb * L * 12);
@@ -576,42 +647,50 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
         VO_CUDA(ctx, cudaMemcpyAsync(di, hp, in_bytes, cudaMemcpyHostToDevice, ms));
         VO_CUDA(ctx, cudaEventRecord(B->done_ev, ctx->stream));
     } else {
+    // Only the landmark keypoints and the counts stand between the call and the first kernel (every DMA operation costs
+    // 5-8 us of latency on top of its bytes): keypoints in place, both count arrays through the staging block as ONE copy;
+    // with prefetched frames the candidate keypoints follow on the io stream (the candidate tracker waits for them),
+    // and so do the landmarks, which only PnP needs.
+    const bool have_cand = Cn > 0 && cand_pts && n_cand;
+    cand_late = have_cand && prefetched;
     VO_CUDA(ctx, upload(o_lmp, lm_pts, (size_t)nb * L * 8, ms));
-    VO_CUDA(ctx, upload(o_nlm, n_lm, (size_t)nb * 4, ms));
-    if (Cn > 0 && cand_pts && n_cand) {
-        VO_CUDA(ctx, upload(o_cp, cand_pts, (size_t)nb * Cn * 8, ms));
-        VO_CUDA(ctx, upload(o_nc, n_cand, (size_t)nb * 4, ms));
-    } else {
-        VO_CUDA(ctx, cudaMemsetAsync(di + o_nc, 0, (size_t)nb * 4, ctx->stream));
-    }
+    memcpy(hp + o_nlm, n_lm, (size_t)nb * 4);
+    if (have_cand) memcpy(hp + o_nc, n_cand, (size_t)nb * 4);
+    else memset(hp + o_nc, 0, (size_t)nb * 4);
+    VO_CUDA(ctx, cudaMemcpyAsync(di + o_nlm, hp + o_nlm, (o_nc - o_nlm) + (size_t)nb * 4, cudaMemcpyHostToDevice, ms));
+    if (have_cand && !cand_late) VO_CUDA(ctx, upload(o_cp, cand_pts, (size_t)nb * Cn * 8, ms));
     VO_CUDA(ctx, cudaEventRecord(B->done_ev, ctx->stream));   // points uploaded; previous step fully retired
-    // the landmarks are only needed by PnP: their upload rides beside the tracker
+    if (host_trace) {
+        VO_TRY(vo_reserve(ctx, B->stamps, 64 * 4 * 8));
+        trace_stamp_kernel<<<1, 1, 0, ctx->stream>>>((unsigned long long*)B->stamps.p + (B->stamp_step & 63) * 4);
+    }
     VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->done_ev, 0));
+    if (cand_late) {
+        VO_CUDA(ctx, upload(o_cp, cand_pts, (size_t)nb * Cn * 8, B->io_stream));
+        VO_CUDA(ctx, cudaEventRecord(B->cand_in_ev, B->io_stream));
+    }
     VO_CUDA(ctx, upload(o_lmo, lm_obj, (size_t)nb * L * 12, B->io_stream));
     VO_CUDA(ctx, cudaEventRecord(B->obj_ev, B->io_stream));
     }
-    // Small (packed) steps are latency-bound: the copy + pyramid launches of the NEXT frame set (a dozen driver calls)
-    // are enqueued after this step's own kernels instead of in front of them.  The side stream must still wait for the
-    // PREVIOUS step's end only (the set it overwrites was that step's `cur`), so that wait is enqueued here, before
-    // batch_finish re-records the event.
+    // The copy + pyramid launches of the NEXT frame set (a dozen driver calls, 30-40 us of host time during which the GPU
+    // would wait for this step's first kernel) are enqueued after this step's own work instead of in front of it; the copy
+    // still queues behind this step's small uploads (done_ev).  The side stream must wait for the PREVIOUS step's end only
+    // (the set it overwrites was that step's `cur`), so that wait is enqueued here, before batch_finish re-records the event.
     bool deferred_prefetch = false;
     if (prefetched) {
-        if (packed) {
-            for (int k = 0; k < B->q_count; ++k) deferred_prefetch = deferred_prefetch || B->q_src[(B->q_head + k) & 1] != nullptr;
-            if (deferred_prefetch) VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->step_end_ev, 0));
-        } else {
-            VO_TRY(batch_issue_prefetch(B, B->done_ev));         // frames of later steps: behind this step's uploads
-        }
+        for (int k = 0; k < B->q_count; ++k) deferred_prefetch = deferred_prefetch || B->q_src[(B->q_head + k) & 1] != nullptr;
+        if (deferred_prefetch) VO_CUDA(ctx, cudaStreamWaitEvent(B->pre_stream, B->step_end_ev, 0));
         VO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B->q_ev[q_slot], 0));
     }
     uint8_t* dq = (uint8_t*)B->outs.p;
     cudaStream_t main_stream = ctx->stream;
+    if (host_trace) h_in = now_us();
     if (prefetched) {
         // pyramids are already there: landmark tracker, then candidate tracker with the pose chain beside it
         VO_TRY(batch_track_pose_overlapped(B, nullptr, (const float*)(di + o_lmp), (const float*)(di + o_lmo), (const int*)(di + o_nlm),
                                            (const float*)(di + o_cp), (const int*)(di + o_nc), (float*)(dq + q_lmn), dq + q_lms,
                                            (float*)(dq + q_cn), dq + q_cs, (double*)(dq + q_pose), dq + q_ok, dq + q_mask,
-                                           (int*)(dq + q_ni), packed ? nullptr : B->obj_ev));
+                                           (int*)(dq + q_ni), packed ? nullptr : B->obj_ev, cand_late ? B->cand_in_ev : nullptr));
     } else {
         // The frames go up chunk by chunk, back to back on the copy stream; chunk k's pyramids + landmark tracker
         // run on a compute stream as soon as its frames have landed (the later chunks are on the wire meanwhile);
@@ -670,6 +749,7 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
         VO_CUDA(ctx, cudaStreamWaitEvent(main_stream, B->pose_ev, 0));
     }
     VO_TRY(batch_finish(B));
+    if (host_trace) h_kern = now_us();
     uint8_t* ho = hp + in_bytes;
     struct OutCopy { void* dst; size_t off, bytes; bool staged; };
     OutCopy outs[8] = {{lm_next, q_lmn, (size_t)nb * L * 8, false}, {lm_status, q_lms, (size_t)nb * L, false},
@@ -689,21 +769,45 @@ extern "C" int b200vo_batch_step(b200vo_batch* B, const uint8_t* frames, const f
     }
     // the tracker's results go home on the io stream while PnP runs; the pose results follow PnP
     VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->lm_ev, 0));
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
         OutCopy& o = outs[i];
-        if (i == 2) VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->cand_ev, 0));
+        if (i == 2) {
+            VO_CUDA(ctx, cudaStreamWaitEvent(B->io_stream, B->cand_ev, 0));
+            if (host_trace && B->stamps.p) trace_stamp_kernel<<<1, 1, 0, B->io_stream>>>((unsigned long long*)B->stamps.p + (B->stamp_step & 63) * 4 + 2);
+        }
         if (!o.dst || o.bytes == 0) continue;
         o.staged = !is_pinned(o.dst);
-        VO_CUDA(ctx, cudaMemcpyAsync(o.staged ? (void*)(ho + o.off) : o.dst, dq + o.off, o.bytes, cudaMemcpyDeviceToHost,
-                                     i < 4 ? B->io_stream : ctx->stream));
+        VO_CUDA(ctx, cudaMemcpyAsync(o.staged ? (void*)(ho + o.off) : o.dst, dq + o.off, o.bytes, cudaMemcpyDeviceToHost, B->io_stream));
     }
+    if (host_trace && B->stamps.p) trace_stamp_kernel<<<1, 1, 0, B->io_stream>>>((unsigned long long*)B->stamps.p + (B->stamp_step & 63) * 4 + 3);
+    // pose | ok | inlier mask | inlier counts are adjacent in the result block: ONE read-back into the staging block
+    // (four DMA operations of a few KB each cost 20-30 us of latency behind the last kernel), host memcpy out
+    for (int i = 4; i < 8; ++i) outs[i].staged = true;
+    VO_CUDA(ctx, cudaMemcpyAsync(ho + q_pose, dq + q_pose, out_bytes - q_pose, cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA(ctx, cudaEventRecord(B->io_ev, B->io_stream));
     VO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B->io_ev, 0));
+    if (host_trace && B->stamps.p) {
+        trace_stamp_kernel<<<1, 1, 0, ctx->stream>>>((unsigned long long*)B->stamps.p + (B->stamp_step & 63) * 4 + 1);
+        B->stamp_step++;
+    }
     VO_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if (deferred_prefetch) VO_TRY(batch_issue_prefetch(B, B->done_ev, false));
+    if (host_trace) h_rb = now_us();
     VO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (host_trace) h_sync = now_us();
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     for (auto& o : outs)
         if (o.dst && o.bytes && o.staged) memcpy(o.dst, ho + o.off, o.bytes);
+    if (host_trace) {
+        const double h_exit = now_us();
+        if (++B->host_calls > 8) {   // the first calls allocate
+            B->host_us[0] += h_in - h_entry; B->host_us[1] += h_kern - h_entry; B->host_us[2] += h_rb - h_entry;
+            B->host_us[3] += h_sync - h_entry; B->host_us[4] += h_exit - h_entry;
+            B->host_us[5] += h_entry - B->host_last_exit;
+            B->host_n++;
+        }
+        B->host_last_exit = h_exit;
+    }
     return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <vector>
 #include "../../include/b200vo.h"
 
 #define VO_MAX_LEVELS 12
@@ -115,6 +116,7 @@ struct KltPointSet {
     uint8_t* status;    // [batch][cap]
     float* err;         // [batch][cap] or nullptr
 };
+void vo_klt_trace_read(b200vo_ctx* ctx, std::vector<unsigned long long>& out);   // B200VO_TRACE_FILE aid
 int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,
                    const uint8_t* d_next_slab, size_t next_stride, int batch, const KltPointSet* sets, int n_sets,
                    int n_fixed, const KltParams& kp);

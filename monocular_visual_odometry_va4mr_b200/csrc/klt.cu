@@ -341,6 +341,16 @@ int vo_klt_launch2(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab
     return 0;
 }
 
+// trace aid (B200VO_TRACE_FILE): (first feature claimed, last warp retired) GPU wall-clock pairs of every queue slot
+void vo_klt_trace_read(b200vo_ctx* ctx, std::vector<unsigned long long>& out)
+{
+    out.clear();
+    if (!ctx->d_klt_queue.p) return;
+    std::vector<unsigned long long> raw((size_t)KLT_QUEUE_SLOTS * KLT_QUEUE_INTS / 2);
+    if (cudaMemcpy(raw.data(), ctx->d_klt_queue.p, raw.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    for (int s = 0; s < KLT_QUEUE_SLOTS; ++s) { out.push_back(raw[(size_t)s * 4 + 1]); out.push_back(raw[(size_t)s * 4 + 2]); }
+}
+
 int vo_klt_launch(b200vo_ctx* ctx, const PyrGeom& g, const uint8_t* d_prev_slab, size_t prev_stride,
                   const uint8_t* d_next_slab, size_t next_stride, int batch, int cap,
                   const int* d_n_pts, int n_fixed, const float* d_pts, float* d_next,

@@ -44,6 +44,12 @@ struct KV3 {
     static constexpr int MIN_CTAS = ((227 * 1024) / (KLT_WARPS * PER_WARP + 64 + 1024) * KLT_WARPS >= 32 ? 32 : 24) / KLT_WARPS;
 };
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void* gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
@@ -163,7 +169,10 @@ klt_kernel_v3(const KltArgs a)
     // ahead lets the first half of the warps claim two features each while the other half of the machine gets none.
     const bool ahead = total >= 2 * (int)gridDim.x * KLT_WARPS;
     int gw = 0;
-    if (lane == 0) gw = atomicAdd(a.queue, 1);
+    if (lane == 0) {
+        gw = atomicAdd(a.queue, 1);
+        if (gw == 0) reinterpret_cast<unsigned long long*>(a.queue)[1] = global_timer_ns();   // trace: first feature claimed
+    }
     gw = __shfl_sync(0xffffffffu, gw, 0);
     while (gw < total) {
         int gw_next = 0;
@@ -479,6 +488,9 @@ klt_kernel_v3(const KltArgs a)
     // the last warp of the grid to find the queue empty re-arms it for the next launch that uses this slot
     if (lane == 0) {
         const int nwarps = (int)gridDim.x * KLT_WARPS;
-        if (atomicAdd(a.queue + 1, 1) == nwarps - 1) { a.queue[0] = 0; a.queue[1] = 0; __threadfence(); }
+        if (atomicAdd(a.queue + 1, 1) == nwarps - 1) {
+            reinterpret_cast<unsigned long long*>(a.queue)[2] = global_timer_ns();                   // trace: last warp retired
+            a.queue[0] = 0; a.queue[1] = 0; __threadfence();
+        }
     }
 }

@@ -249,7 +249,16 @@ pnp_select_kernel(PnpArgs a)
 // optional phase stamps (clock64 of thread 0) for benchmarks/pose_phases.py: PnpArgs::phase_clk, [batch][16]
 __device__ __forceinline__ void phase_stamp(const PnpArgs& a, int b, int k)
 {
-    if (a.phase_clk && threadIdx.x == 0) a.phase_clk[(size_t)b * 16 + k] = clock64();
+    if (a.phase_clk && threadIdx.x == 0) {
+        a.phase_clk[(size_t)b * 16 + k] = clock64();
+        if (k == 0 || k == 8) {   // wall-clock stamps + SM id: where the CTA ran beside the tracker (B200VO_TRACE_FILE)
+            unsigned long long t; unsigned sm;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            a.phase_clk[(size_t)b * 16 + (k == 0 ? 12 : 14)] = (long long)t;
+            a.phase_clk[(size_t)b * 16 + 13] = sm;
+        }
+    }
 }
 
 #define EPNP_T 256
