@@ -733,6 +733,9 @@ def main(argv=None):
     if world > 1:
         affinity = guarded(pin_to_gpu_cores, local)     # each rank on the cores (NUMA node) next to its GPU: its page-locked pool lands there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif os.environ.get("B200VO_FORCE_NCCL"):   # A/B switch: a one-rank process group, to see what NCCL's presence alone costs
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
     from monocular_visual_odometry_va4mr_b200 import _lib, sharding
     ctx = _lib.Context(local)
     if n_local <= 0:
