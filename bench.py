@@ -724,6 +724,12 @@ def main(argv=None):
         return
 
     # ---------------- B200 arm ----------------
+    if world > 1:
+        # A rank's step uses four streams at once (landmark tracker + pose chain, candidate tracker, pyramid prefetch,
+        # read-backs) and CUDA maps streams onto 8 hardware queues by default; NCCL's own streams shift that mapping, and two
+        # of the step's streams on one queue serialise (head-of-line blocking) -- the suspected reason for the 0.08 ms per
+        # step a shard loses under torchrun.  One queue per stream; read by the driver at initialisation.
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -802,7 +808,7 @@ def main(argv=None):
                                         "b200vo_batch_step_dev(frames=NULL)" if not args.no_lookahead else "b200vo_batch_step_dev(frames)"),
                            parallelism=f"sequences sharded x{world} ({args.scaling} scaling), NCCL all_gather of poses"),
             "clocks": clocks,
-            "cpu_affinity_cores": affinity,
+            "cpu_affinity_cores": affinity, "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
             "e2e": e2e,
             "gpu_launches": res["launches"],
             "roofline": roofline,
