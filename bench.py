@@ -673,7 +673,9 @@ def klt_roofline(args, opts, wl, res, roofline_note):
             "avg_launch_ms_source": f"CUDA events on the launching stream over {res.get('profiled_steps', 0)} steps of the same loop run right behind "
                                     "the timed region (timing events between the launches stall the timed loop itself by 2-12 %)",
             "stage_ms_per_step": {"pyramid": float(res["stage_ms"][0]) / nprof, "klt_landmarks": klt_ms,
-                                  "pose_chain_beside_klt_candidates": float(res["stage_ms"][2]) / nprof},
+                                  "pose_chain_beside_klt_candidates": float(res["stage_ms"][2]) / nprof,
+                                  "pose_stage_note": "event behind the pose kernel, stamped when its stream is serviced again; on the kernels' own "
+                                                     "clock (B200VO_TRACE_FILE) the pose CTAs finish 0.14 ms after the landmark launch at 64 sequences"},
             "note": roofline_note}, levels
 
 
